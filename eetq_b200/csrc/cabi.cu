@@ -1,0 +1,217 @@
+// cabi.cu -- the extern "C" boundary of libeetq_b200.so (declared in include/eetq_b200.h).
+//
+// Stands in for the reference's torch/pybind boundary:
+//   /root/reference/csrc/eetpy.cpp:7-19                                  (the 4 hot-path symbols)
+//   /root/reference/csrc/cutlass_kernels/fpA_intB_gemm_wrapper.cu:28-202 (marshalling + M-based dispatch)
+// Differences by design: raw pointers + explicit stream instead of torch::Tensor; argument validation the
+// reference lacks; error codes + thread-local message instead of C++ exceptions/asserts;
+// per-device attributes cached once instead of re-queried per forward (fpA_intB_gemm_template.h:390-397).
+#include <atomic>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace eetq_b200 {
+
+namespace {
+thread_local char tls_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tls_error, sizeof(tls_error), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(uint64_t(n), std::memory_order_relaxed); }
+
+const DeviceInfo& device_info()
+{
+    static DeviceInfo infos[64];
+    static std::once_flag flags[64];
+    static DeviceInfo bad;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return bad;
+    std::call_once(flags[dev], [dev]() {
+        DeviceInfo d;
+        bool ok = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
+        ok      = ok && cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess;
+        ok      = ok && cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev) == cudaSuccess;
+        ok      = ok && cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess;
+        d.ok    = ok;
+        infos[dev] = d;
+    });
+    return infos[dev];
+}
+
+namespace {
+
+int check_arch()
+{
+    const DeviceInfo& di = device_info();
+    if (!di.ok) {
+        set_error("could not query the current CUDA device");
+        return EETQ_B200_ECUDA;
+    }
+    if (di.cc_major != 10) {
+        set_error("libeetq_b200 is built for sm_100a only; current device is sm_%d%d", di.cc_major, di.cc_minor);
+        return EETQ_B200_EARCH;
+    }
+    return EETQ_B200_OK;
+}
+
+int check_kn(const char* who, int64_t K, int64_t N)
+{
+    if (K <= 0 || N <= 0 || (K % 64) != 0 || (N % 64) != 0) {
+        set_error("%s: K (%lld) and N (%lld) must be positive multiples of 64", who, (long long)K, (long long)N);
+        return EETQ_B200_EINVAL;
+    }
+    if (K > (1 << 20) || N > (1 << 24)) {
+        set_error("%s: K (%lld) or N (%lld) too large", who, (long long)K, (long long)N);
+        return EETQ_B200_EINVAL;
+    }
+    return EETQ_B200_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace eetq_b200
+
+using namespace eetq_b200;
+
+extern "C" {
+
+const char* eetq_b200_last_error(void) { return tls_error; }
+int eetq_b200_version(void) { return EETQ_B200_VERSION; }
+uint64_t eetq_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int eetq_b200_quantize(const void* w_kn, int w_dtype, int64_t K, int64_t N, int8_t* q_b200, void* scales, float* s32,
+                       int8_t* q_kn, void* stream)
+{
+    EB_CHECK_ARG(w_kn && q_b200 && scales && s32, "quantize: null pointer argument");
+    EB_CHECK_ARG(aligned16(w_kn) && aligned16(q_b200) && (q_kn == nullptr || aligned16(q_kn)),
+                 "quantize: pointers must be 16-byte aligned");
+    if (int rc = check_kn("quantize", K, N))
+        return rc;
+    if (int rc = check_arch())
+        return rc;
+    return launch_quantize(w_kn, w_dtype, K, N, q_b200, scales, s32, q_kn, static_cast<cudaStream_t>(stream));
+}
+
+int eetq_b200_pack(const int8_t* q_kn, int64_t K, int64_t N, int8_t* q_b200, void* stream)
+{
+    EB_CHECK_ARG(q_kn && q_b200, "pack: null pointer argument");
+    EB_CHECK_ARG(aligned16(q_kn) && aligned16(q_b200), "pack: pointers must be 16-byte aligned");
+    if (int rc = check_kn("pack", K, N))
+        return rc;
+    if (int rc = check_arch())
+        return rc;
+    return launch_transpose_bytes(q_kn, K, N, q_b200, static_cast<cudaStream_t>(stream));
+}
+
+int eetq_b200_unpack(const int8_t* q_b200, int64_t K, int64_t N, int8_t* q_kn, void* stream)
+{
+    EB_CHECK_ARG(q_kn && q_b200, "unpack: null pointer argument");
+    EB_CHECK_ARG(aligned16(q_kn) && aligned16(q_b200), "unpack: pointers must be 16-byte aligned");
+    if (int rc = check_kn("unpack", K, N))
+        return rc;
+    if (int rc = check_arch())
+        return rc;
+    return launch_transpose_bytes(q_b200, N, K, q_kn, static_cast<cudaStream_t>(stream));
+}
+
+int eetq_b200_from_ref_layout(const uint8_t* w_ref, int64_t K, int64_t N, int8_t* q_b200, void* stream)
+{
+    EB_CHECK_ARG(w_ref && q_b200, "from_ref_layout: null pointer argument");
+    EB_CHECK_ARG(aligned16(w_ref) && aligned16(q_b200), "from_ref_layout: pointers must be 16-byte aligned");
+    if (int rc = check_kn("from_ref_layout", K, N))
+        return rc;
+    if (int rc = check_arch())
+        return rc;
+    return launch_from_ref_layout(w_ref, K, N, q_b200, static_cast<cudaStream_t>(stream));
+}
+
+int eetq_b200_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t* w_ref, void* stream)
+{
+    EB_CHECK_ARG(w_ref && q_b200, "to_ref_layout: null pointer argument");
+    EB_CHECK_ARG(aligned16(w_ref) && aligned16(q_b200), "to_ref_layout: pointers must be 16-byte aligned");
+    if (int rc = check_kn("to_ref_layout", K, N))
+        return rc;
+    if (int rc = check_arch())
+        return rc;
+    return launch_to_ref_layout(q_b200, K, N, w_ref, static_cast<cudaStream_t>(stream));
+}
+
+size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K)
+{
+    if (M <= 0 || N <= 0 || K <= 0)
+        return 0;
+    return gemm_tc_workspace_bytes(M, N, K);
+}
+
+int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
+                            void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
+                            size_t workspace_bytes, int flags, void* stream)
+{
+    EB_CHECK_ARG(x && w_b200 && scales && y, "w8a16_gemm: null pointer argument");
+    EB_CHECK_ARG(dtype == EETQ_B200_F16 || dtype == EETQ_B200_BF16, "w8a16_gemm: dtype must be F16 or BF16 (got %d)",
+                 dtype);
+    EB_CHECK_ARG(M >= 0 && M <= (int64_t(1) << 24), "w8a16_gemm: bad M=%lld", (long long)M);
+    if (int rc = check_kn("w8a16_gemm", K, N))
+        return rc;
+    EB_CHECK_ARG(ldx >= K && ldy >= N, "w8a16_gemm: ldx (%lld) < K or ldy (%lld) < N", (long long)ldx, (long long)ldy);
+    EB_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0, "w8a16_gemm: ldx and ldy must be multiples of 8 elements");
+    EB_CHECK_ARG(aligned16(x) && aligned16(w_b200) && aligned16(y), "w8a16_gemm: x, w and y must be 16-byte aligned");
+    EB_CHECK_ARG(!((flags & EETQ_B200_FLAG_FORCE_GEMV) && (flags & EETQ_B200_FLAG_FORCE_TC)),
+                 "w8a16_gemm: FORCE_GEMV and FORCE_TC are exclusive");
+    if (M == 0)
+        return EETQ_B200_OK;  // empty batch: nothing to enqueue
+    if (int rc = check_arch())
+        return rc;
+
+    const bool pdl = (flags & EETQ_B200_FLAG_PDL) != 0;
+    bool use_gemv  = M <= 4;  // same cut as the reference's SMALL_M_FAST_PATH (fpA_intB_gemm_wrapper.h:4)
+    if (flags & EETQ_B200_FLAG_FORCE_GEMV) {
+        EB_CHECK_ARG(M <= EETQ_B200_GEMV_MAX_M, "w8a16_gemm: FORCE_GEMV needs M <= %d", EETQ_B200_GEMV_MAX_M);
+        use_gemv = true;
+    }
+    if (flags & EETQ_B200_FLAG_FORCE_TC)
+        use_gemv = false;
+
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (use_gemv)
+        return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, pdl, s);
+    return launch_gemm_tc(x, ldx, w_b200, scales, bias, y, ldy, M, N, K, dtype, workspace, workspace_bytes, pdl, s);
+}
+
+int eetq_b200_w8a16_gemm(const void* x, const int8_t* w_b200, const void* scales, const void* bias, void* y, int64_t M,
+                         int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream)
+{
+    return eetq_b200_w8a16_gemm_ex(x, K, w_b200, scales, bias, y, N, M, N, K, dtype, workspace, workspace_bytes,
+                                   EETQ_B200_FLAG_DEFAULT, stream);
+}
+
+int eetq_b200_w8a16_gemm_host(const void* x_host, void* x_dev, const int8_t* w_b200, const void* scales,
+                              const void* bias, void* y_dev, void* y_host, int64_t M, int64_t N, int64_t K, int dtype,
+                              void* workspace, size_t workspace_bytes, void* stream)
+{
+    EB_CHECK_ARG(x_host && x_dev && y_dev && y_host, "w8a16_gemm_host: null pointer argument");
+    EB_CHECK_ARG(M >= 0 && N > 0 && K > 0, "w8a16_gemm_host: bad shape");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (M == 0)
+        return EETQ_B200_OK;
+    EB_CHECK_CUDA(cudaMemcpyAsync(x_dev, x_host, size_t(M) * K * 2, cudaMemcpyHostToDevice, s));
+    if (int rc = eetq_b200_w8a16_gemm(x_dev, w_b200, scales, bias, y_dev, M, N, K, dtype, workspace, workspace_bytes,
+                                      stream))
+        return rc;
+    EB_CHECK_CUDA(cudaMemcpyAsync(y_host, y_dev, size_t(M) * N * 2, cudaMemcpyDeviceToHost, s));
+    return EETQ_B200_OK;
+}
+
+}  // extern "C"

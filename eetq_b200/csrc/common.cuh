@@ -1,0 +1,102 @@
+// common.cuh -- shared host/device helpers for libeetq_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/eetq_b200.h"
+
+namespace eetq_b200 {
+
+// ---- error plumbing (thread-local message, never abort) -------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define EB_CHECK_ARG(cond, ...)                                                                                        \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            ::eetq_b200::set_error(__VA_ARGS__);                                                                       \
+            return EETQ_B200_EINVAL;                                                                                   \
+        }                                                                                                              \
+    } while (0)
+
+#define EB_CHECK_CUDA(expr)                                                                                            \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess) {                                                                                       \
+            ::eetq_b200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);        \
+            return EETQ_B200_ECUDA;                                                                                    \
+        }                                                                                                              \
+    } while (0)
+
+// per-device properties, fetched once (the reference re-queries these on every forward call,
+// fpA_intB_gemm_template.h:390-397)
+struct DeviceInfo {
+    int sm_count     = 0;
+    int cc_major     = 0;
+    int cc_minor     = 0;
+    int max_smem_optin = 0;
+    bool ok          = false;
+};
+const DeviceInfo& device_info();  // for the current device; ok == false if the query failed
+
+// ---- launchers implemented in the .cu files ---------------------------------------------------------
+int launch_quantize(const void* w_kn, int w_dtype, int64_t K, int64_t N, int8_t* q_b200, void* scales, float* s32,
+                    int8_t* q_kn, cudaStream_t stream);
+int launch_transpose_bytes(const int8_t* src, int64_t rows, int64_t cols, int8_t* dst, cudaStream_t stream);
+int launch_from_ref_layout(const uint8_t* w_ref, int64_t K, int64_t N, int8_t* q_b200, cudaStream_t stream);
+int launch_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t* w_ref, cudaStream_t stream);
+
+int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
+                int M, int64_t N, int64_t K, int dtype, bool pdl, cudaStream_t stream);
+
+size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y,
+                   int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes,
+                   bool pdl, cudaStream_t stream);
+
+// ---- small device helpers ----------------------------------------------------------------------------
+template <typename T>
+struct DTypeOf;
+template <>
+struct DTypeOf<__half> {
+    static constexpr int value = EETQ_B200_F16;
+};
+template <>
+struct DTypeOf<__nv_bfloat16> {
+    static constexpr int value = EETQ_B200_BF16;
+};
+
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_float(float v) { return v; }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+
+// 128-bit streaming load that does not allocate in L1 (weights are read exactly once)
+__device__ __forceinline__ uint4 ldg_stream_128(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// programmatic dependent launch (PDL) controls; no-ops when the kernel was launched without the attribute
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+}  // namespace eetq_b200

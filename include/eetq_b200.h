@@ -1,0 +1,137 @@
+/*
+ * eetq_b200.h -- C ABI of libeetq_b200.so: the B200 (sm_100a) w8a16 weight-only GEMM path.
+ *
+ * This is the drop-in boundary for the ONE hot path of NetEase-FuXi/EETQ that this repository
+ * replaces.  Each entry point names the reference interface it stands in for (paths relative to
+ * the EETQ tree).  The reference exposes the path through a pybind11 torch extension
+ * (csrc/eetpy.cpp:7-19); here the same operations are plain C functions over raw device pointers,
+ * sizes and a cudaStream_t, so that any host language can bind them (ctypes stub shown in
+ * INTEGRATION.md; eetq_b200/_cabi.py is the one this repository ships).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers on the CURRENT CUDA device unless a name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Every call only
+ *     ENQUEUES work: no synchronisation, no allocation -> all calls are CUDA-graph capturable
+ *     (the reference enqueues on at::cuda::getCurrentCUDAStream, fpA_intB_gemm_wrapper.cu:151).
+ *   - Return value: 0 on success, a negative EETQ_B200_E* code on failure; the message is available
+ *     from eetq_b200_last_error() (thread-local).  Nothing ever aborts (the reference throws
+ *     std::runtime_error / asserts: csrc/utils/cuda_utils.h:29-51, weightOnlyBatchedGemv/kernelLauncher.cu:124-127).
+ *   - Logical shapes follow the reference: x [M,K] row-major activations, logical weight Wq int8 [K,N]
+ *     (K = in_features, N = out_features), scales [N], y [M,N] row-major.
+ *   - "b200 layout" (DESIGN.md section 3): the K*N weight bytes stored output-feature-major,
+ *     w_b200[n*K + k] = Wq[k, n], plain signed int8.  It replaces the reference's sm80 interleaved
+ *     layout (cutlass_preprocessors.cc:497-534).  Requires K % 64 == 0 and N % 64 == 0 exactly like the
+ *     reference (cutlass_preprocessors.cc:230,455; fpA_intB_gemm_template.h:139-142).
+ */
+#ifndef EETQ_B200_H_
+#define EETQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EETQ_B200_VERSION 100 /* 0.1.0 */
+
+/* activation / weight element types */
+enum {
+    EETQ_B200_F16  = 0,
+    EETQ_B200_BF16 = 1, /* extension: the reference silently reinterprets bf16 as fp16 (fpA_intB_gemm_wrapper.cu:141-144) */
+    EETQ_B200_F32  = 2  /* quantiser input only */
+};
+
+/* error codes */
+enum {
+    EETQ_B200_OK        = 0,
+    EETQ_B200_EINVAL    = -1, /* bad argument (null pointer, unsupported dtype, shape constraint) */
+    EETQ_B200_ECUDA     = -2, /* a CUDA runtime/driver call failed */
+    EETQ_B200_EARCH     = -3, /* not an sm_100 device */
+    EETQ_B200_EWORKSPACE = -4 /* workspace too small */
+};
+
+/* flags for eetq_b200_w8a16_gemm_ex */
+enum {
+    EETQ_B200_FLAG_DEFAULT    = 0,
+    EETQ_B200_FLAG_FORCE_GEMV = 1, /* force the SIMT streaming kernel (M <= EETQ_B200_GEMV_MAX_M) */
+    EETQ_B200_FLAG_FORCE_TC   = 2, /* force the tcgen05 kernel */
+    EETQ_B200_FLAG_PDL        = 4  /* launch with programmatic-dependent-launch attribute */
+};
+
+#define EETQ_B200_GEMV_MAX_M 8
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* eetq_b200_last_error(void);
+int         eetq_b200_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Q1  quant_weights  -- replaces symmetric_quantize_last_axis_of_tensor
+ *     (csrc/cutlass_kernels/fpA_intB_gemm_wrapper.cu:28-107 -> ft::symmetric_quantize,
+ *      cutlass_preprocessors.cc:581-678), on the GPU, bit-exact:
+ *       amax[n] = max_k |float(w[k,n])| ; s32[n] = amax[n] * (1/128)
+ *       q[k,n]  = int8(clamp(round_half_away(float(w[k,n]) / s32[n]), -128, 127))
+ *       scales[n] = (w dtype)(s32[n])            (all-zero column -> q = 127, scale 0, like the reference)
+ *   w_kn      [K,N] row-major, dtype w_dtype (F16 / BF16 / F32)
+ *   q_b200    out, K*N bytes in b200 layout (the "processed" tensor of the reference API)
+ *   scales    out, [N] in w_dtype
+ *   s32       out, [N] fp32 scales (also used as the abs-max workspace) -- required
+ *   q_kn      out or NULL, [K,N] row-major int8 (the "unprocessed" tensor of the reference API)
+ * ------------------------------------------------------------------------------------------- */
+int eetq_b200_quantize(const void* w_kn, int w_dtype, int64_t K, int64_t N, int8_t* q_b200, void* scales, float* s32,
+                       int8_t* q_kn, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Q2  preprocess_weights  -- replaces preprocess_weights_cuda (fpA_intB_gemm_wrapper.cu:109-128 ->
+ *     ft::preprocess_weights, cutlass_preprocessors.cc:536-544): row-major int8 [K,N] -> b200 layout.
+ * ------------------------------------------------------------------------------------------- */
+int eetq_b200_pack(const int8_t* q_kn, int64_t K, int64_t N, int8_t* q_b200, void* stream);
+/* inverse (b200 layout -> row-major int8 [K,N]); no reference counterpart, used by tests/tools */
+int eetq_b200_unpack(const int8_t* q_b200, int64_t K, int64_t N, int8_t* q_kn, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Q3  checkpoint compatibility: convert between the reference's sm75..sm89 interleaved bytes
+ *     (what EETQ / HF `EetqLinear.weight` checkpoints store; preprocess_weights_for_mixed_gemm,
+ *     cutlass_preprocessors.cc:497-534) and the b200 layout.
+ * ------------------------------------------------------------------------------------------- */
+int eetq_b200_from_ref_layout(const uint8_t* w_ref, int64_t K, int64_t N, int8_t* q_b200, void* stream);
+int eetq_b200_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t* w_ref, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * D1  w8_a16_gemm / w8_a16_gemm_  -- replaces w8_a16_gemm_forward_cuda(_)
+ *     (fpA_intB_gemm_wrapper.cu:130-202) including its M-based dispatch (SMALL_M_FAST_PATH,
+ *     fpA_intB_gemm_wrapper.h:4): small M -> SIMT streaming kernel (replaces weight_only_batched_gemv,
+ *     weightOnlyBatchedGemv/kernel.h:294-468), larger M -> tcgen05 kernel (replaces the CUTLASS
+ *     fpA_intB GEMM, cutlass_extensions/.../fpA_intB_gemm.h:60-486).
+ *       y[m,n] = dtype( sum_k x[m,k] * q[k,n] * s[n] ) (+ bias[n], fused; the reference adds bias with a
+ *       separate torch op, python/eetq/modules/qlinear.py:61)
+ *   x [M,K] dtype, row stride ldx elements (ldx >= K; pass K for contiguous)
+ *   w_b200 K*N int8 in b200 layout;  scales [N] dtype;  bias [N] dtype or NULL
+ *   y [M,N] dtype, row stride ldy elements
+ *   workspace: eetq_b200_workspace_bytes(M,N,K) bytes, ZERO-INITIALISED ONCE by the caller (the kernels
+ *   leave it zeroed); may be NULL when that function returns 0.  One workspace must not be shared by
+ *   calls that can run concurrently.
+ * ------------------------------------------------------------------------------------------- */
+size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K);
+
+int eetq_b200_w8a16_gemm(const void* x, const int8_t* w_b200, const void* scales, const void* bias, void* y, int64_t M,
+                         int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
+                            void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
+                            size_t workspace_bytes, int flags, void* stream);
+
+/* Convenience for hosts without their own device-memory plumbing: x_host / y_host are HOST buffers
+ * (pinned for true async); the call stages them through the caller-provided device scratch
+ * x_dev [M*K], y_dev [M*N] on `stream` (H2D copy, kernel, D2H copy; no synchronisation). */
+int eetq_b200_w8a16_gemm_host(const void* x_host, void* x_dev, const int8_t* w_b200, const void* scales,
+                              const void* bias, void* y_dev, void* y_host, int64_t M, int64_t N, int64_t K, int dtype,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernels this library has launched on this process so far (bench.py's gpu_launches) */
+uint64_t eetq_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EETQ_B200_H_ */

@@ -1,0 +1,89 @@
+"""CPU tests of the host-side mirror of the reference's Python surface (no kernels run)."""
+import pytest
+import torch
+import torch.nn as nn
+
+import eetq_b200
+from eetq_b200 import EetqLinear, W8A16Linear, find_layers, set_op_by_name
+from eetq_b200.utils.base import find_submodule, get_named_linears
+
+
+class Block(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.q_proj = nn.Linear(64, 64, bias=False)
+        self.mlp = nn.Sequential(nn.Linear(64, 128), nn.SiLU(), nn.Linear(128, 64))
+
+
+class Tiny(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.layers = nn.ModuleList([Block(), Block()])
+        self.lm_head = nn.Linear(64, 100, bias=False)
+
+
+def test_surface_names_match_reference():
+    # the names the reference exports for the hot path (python/eetq/__init__.py, csrc/eetpy.cpp:9-17)
+    for name in ["W8A16Linear", "EetqLinear", "EetqLinearMMFunction", "quantize_and_preprocess_weights", "eet_quantize",
+                 "find_layers", "set_op_by_name", "quant_weights", "preprocess_weights", "w8_a16_gemm", "w8_a16_gemm_"]:
+        assert hasattr(eetq_b200, name), name
+    import EETQ
+
+    for name in ["quant_weights", "preprocess_weights", "w8_a16_gemm", "w8_a16_gemm_"]:
+        assert hasattr(EETQ, name)
+
+
+def test_find_layers_skips_lm_head():
+    m = Tiny()
+    found = find_layers(m)
+    assert "lm_head" not in found
+    assert sorted(found) == ["layers.0.mlp.0", "layers.0.mlp.2", "layers.0.q_proj", "layers.1.mlp.0", "layers.1.mlp.2",
+                             "layers.1.q_proj"]
+    assert sorted(get_named_linears(m)) == sorted(found)
+    assert find_submodule(m, "layers") is m.layers
+
+
+def test_set_op_by_name_handles_indices():
+    m = Tiny()
+    new = nn.Identity()
+    set_op_by_name(m, "layers.1.mlp.0", new)
+    assert m.layers[1].mlp[0] is new
+    set_op_by_name(m, "lm_head", new)
+    assert m.lm_head is new
+
+
+def test_w8a16linear_buffers_and_state_dict_keys():
+    q = W8A16Linear(128, 64, bias=True, dev="cpu")
+    sd = q.state_dict()
+    assert sorted(sd) == ["bias", "qweight", "weight_scales"]            # qlinear.py:34-38
+    assert sd["qweight"].shape == (128, 64) and sd["qweight"].dtype == torch.int8
+    assert sd["weight_scales"].shape == (64,) and sd["weight_scales"].dtype == torch.float16
+    q2 = W8A16Linear(128, 64, bias=False, dev="cpu")
+    assert q2.bias is None and sorted(q2.state_dict()) == ["qweight", "weight_scales"]
+
+
+def test_eetqlinear_late_scale_registration():
+    q = EetqLinear(128, 64, bias=False, device="cpu")
+    assert sorted(q.state_dict()) == ["weight"]                          # qlinear.py:103
+    q.register_scale("cpu")
+    assert sorted(q.state_dict()) == ["weight", "weight_scales"]         # qlinear.py:113-116
+
+
+def test_eet_quantize_init_only_builds_skeleton():
+    m = Tiny().half()
+    eetq_b200.eet_quantize(m, init_only=True)
+    assert isinstance(m.layers[0].q_proj, W8A16Linear) and isinstance(m.layers[1].mlp[2], W8A16Linear)
+    assert isinstance(m.lm_head, nn.Linear)                              # excluded (quantizer.py:40)
+    assert m.layers[0].mlp[0].bias is not None and m.layers[0].q_proj.bias is None
+
+
+def test_argument_validation_before_any_launch():
+    x = torch.zeros(1, 64, dtype=torch.float32)
+    w = torch.zeros(64, 64, dtype=torch.int8)
+    s = torch.zeros(64, dtype=torch.float16)
+    with pytest.raises(RuntimeError):
+        eetq_b200.w8_a16_gemm(x, w, s)
+    with pytest.raises(RuntimeError, match="int4 or int8"):
+        eetq_b200.quant_weights(torch.zeros(64, 64, dtype=torch.float16), torch.int32, False)
+    with pytest.raises(NotImplementedError):
+        eetq_b200.preprocess_weights(w, is_int4=True)
