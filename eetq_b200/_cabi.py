@@ -40,6 +40,12 @@ SIGNATURES = {
                                          _c_vp, _c_sz, _c_int, _c_vp]),
     "eetq_b200_w8a16_gemm_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int,
                                            _c_vp, _c_sz, _c_vp]),
+    "eetq_b200_w8a16_gemv_fused": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp, _c_i64, _c_vp,
+                                            _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
+    "eetq_b200_decode_embed": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
+    "eetq_b200_decode_rmsnorm": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_int, _c_vp]),
+    "eetq_b200_decode_rope_append": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
+    "eetq_b200_decode_attention": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp]),
 }
 
 

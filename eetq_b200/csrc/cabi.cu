@@ -186,7 +186,7 @@ int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, co
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (use_gemv)
-        return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, pdl, s);
+        return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, GemvExtras{}, pdl, s);
     return launch_gemm_tc(x, ldx, w_b200, scales, bias, y, ldy, M, N, K, dtype, workspace, workspace_bytes, pdl, s);
 }
 

@@ -52,8 +52,16 @@ int launch_transpose_bytes(const int8_t* src, int64_t rows, int64_t cols, int8_t
 int launch_from_ref_layout(const uint8_t* w_ref, int64_t K, int64_t N, int8_t* q_b200, cudaStream_t stream);
 int launch_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t* w_ref, cudaStream_t stream);
 
+enum { GEMV_X_PLAIN = 0, GEMV_X_RMSNORM = 1, GEMV_X_SILU_MUL = 2 };
+struct GemvExtras {
+    const void* norm_weight = nullptr;  // [K], GEMV_X_RMSNORM
+    const void* residual    = nullptr;  // [M, N] row stride ldr
+    int64_t ldr             = 0;
+    float eps               = 0.f;
+    int xmode               = GEMV_X_PLAIN;
+};
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
-                int M, int64_t N, int64_t K, int dtype, bool pdl, cudaStream_t stream);
+                int M, int64_t N, int64_t K, int dtype, const GemvExtras& ex, bool pdl, cudaStream_t stream);
 
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y,

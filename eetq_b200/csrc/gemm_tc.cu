@@ -166,13 +166,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int is_bf16, int umma_m, int u
 
 // ------------------------------------------------------------------------------------------------- dequant
 // 16 int8 (one uint4) -> 16 fp16/bf16 (two uint4).
-//   fp16: PRMT each byte (biased to unsigned) under the exponent of 1024 -> 1024+u, subtract 1152 -> q exactly,
+//   fp16: PRMT each (biased) byte under the exponent of 1024 -> 1024+u, subtract 1152 -> q exactly,
 //         multiply by the channel scale in fp16 (one rounding) == reference arithmetic.
 //   bf16: PRMT into the mantissa of 2^23 (fp32), subtract, pack to bf16 (exact: |q| <= 128).
 template <typename T>
 __device__ __forceinline__ void dequant16(const uint4& in, uint32_t scale2, uint4& out0, uint4& out1)
 {
-    const uint32_t w[4] = {in.x ^ 0x80808080u, in.y ^ 0x80808080u, in.z ^ 0x80808080u, in.w ^ 0x80808080u};
+    const uint32_t w[4] = {in.x, in.y, in.z, in.w};  // biased bytes u = q + 128 (b200 layout)
     uint32_t o[8];
     if constexpr (DTypeOf<T>::value == EETQ_B200_F16) {
         const __half2 bias = __half2half2(__ushort_as_half(0x6480));  // 1152
@@ -589,7 +589,12 @@ int launch_tc_bt(const CUtensorMap& map_w, const CUtensorMap& map_x, const TcPar
     }
 }
 
-size_t counters_bytes(const TcConfig& c) { return (size_t(c.n_tiles) * c.t_tiles * sizeof(int) + 255) & ~size_t(255); }
+// The tile counters live in a FIXED-size region at the start of the workspace so that calls with different
+// (M, N, K) -- hence different partial-buffer layouts -- can share one zero-initialised workspace: only the counter
+// region must stay zero between calls, and every kernel leaves it zero.  Split-K is only chosen when
+// tiles <= 296, so 4 KiB (1024 counters) is always enough.
+constexpr size_t kCounterRegionBytes = 4096;
+size_t counters_bytes(const TcConfig&) { return kCounterRegionBytes; }
 
 }  // namespace
 

@@ -5,17 +5,21 @@
 //   (dispatch: weightOnlyBatchedGemv/kernelLauncher.cu:165-199, called from fpA_intB_gemm_wrapper.cu:149-160)
 // with a design sized for B200's HBM3e rather than a translation of it:
 //
-//   * weights are in the b200 layout (row n = the K int8 of output feature n, contiguous), so a CTA streams
-//     whole rows with perfectly coalesced 128-bit loads; thread t of the CTA owns the 16-byte K-chunks
-//     {t, t+THREADS, ...} of EVERY row and keeps the matching activation slice in fp32 REGISTERS (XREG) --
-//     the weights flow HBM -> registers -> FMA with no shared-memory hop and zero activation re-reads;
+//   * weights are in the b200 layout (row n = the K biased bytes u = q + 128 of output feature n, contiguous),
+//     so a CTA streams whole rows with perfectly coalesced 128-bit loads; thread t of the CTA owns the 16-byte
+//     K-chunks {t, t+256, ...} of EVERY row and keeps the matching activation slice in REGISTERS (packed fp16:
+//     8 registers per 16 values) -- weights flow HBM -> registers -> FMA with no shared-memory hop and zero
+//     activation re-reads;
 //   * rows are processed R at a time, register double-buffered: 2 x R x KITERS 16-byte loads in flight per
-//     thread (256 B/thread, ~128 KB/SM at 2 CTAs/SM) which is what Little's law needs to cover ~6.5 TB/s;
-//   * int8 -> fp32 conversion is exact (PRMT into the mantissa of 2^23, one FADD), products/accumulation are
-//     fp32 (packed FFMA2), the per-channel scale is applied ONCE per output in the epilogue together with the
-//     optional bias; the reference multiplies every weight by the scale in fp16 and accumulates in fp16
-//     (kernel.h:355-377, :425-435), so this kernel is strictly more accurate -- parity is checked against the
-//     fp32-accumulation oracle at 1e-3 norm-relative (tests/test_gemm_gpu.py);
+//     thread (256 B/thread, ~128 KB/SM at 2 CTAs/SM), which is what Little's law needs to cover ~6.5 TB/s;
+//   * fp16 inner loop = 1 PRMT + 2 FHFMA per 2 weights and NO int->float conversion: PRMT drops each byte under
+//     the fp16 exponent byte 0x64, giving fp16(1024 + u) for free; FHFMA (fma.rn.f32.f16, new on sm_100)
+//     multiplies it with the fp16 activation and accumulates in fp32 -- products are exact (11 x 11 bits) and the
+//     constant (1024 + 128) * sum(x) is subtracted once per row.  The per-channel scale is applied ONCE per
+//     output in the epilogue with the optional bias.  The reference multiplies every weight by the scale in fp16
+//     and accumulates in fp16 per thread (kernel.h:355-377, :425-435), so this kernel is strictly more
+//     accurate -- parity is checked against the fp32-accumulation oracle at 1e-3 norm-relative
+//     (tests/test_gemm_gpu.py).  bf16 activations (extension) use an fp32 mantissa-trick + FFMA2 path;
 //   * per-row partial sums are reduced with a transposing warp butterfly (9 shuffles per 8 rows instead of
 //     40) and one shared-memory pass at the end of the CTA;
 //   * the grid is a multiple of the SM count and rows are split evenly (+-1) over CTAs;
@@ -42,43 +46,184 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
     return *reinterpret_cast<float2*>(&rd);
 }
 
-// 4 signed int8 packed in a word -> 4 exact fp32 values.
-// CVT == 0: byte-select I2F.   CVT == 1: bias to unsigned, PRMT the byte into the mantissa of 2^23, subtract.
-template <int CVT>
-__device__ __forceinline__ void cvt4(uint32_t w, float2& lo, float2& hi)
+// acc(fp32) += a(fp16) * b(fp16): one FHFMA on sm_100a (exact 22-bit product, single fp32 rounding)
+__device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float acc)
 {
-    if constexpr (CVT == 0) {
-        lo.x = float(int(int8_t(w & 0xffu)));
-        lo.y = float(int(int8_t((w >> 8) & 0xffu)));
-        hi.x = float(int(int8_t((w >> 16) & 0xffu)));
-        hi.y = float(int(int8_t(w >> 24)));
-    }
-    else {
-        const uint32_t u = w ^ 0x80808080u;
-        lo.x             = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7650)) - 8388736.f;
-        lo.y             = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7651)) - 8388736.f;
-        hi.x             = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7652)) - 8388736.f;
-        hi.y             = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7653)) - 8388736.f;
-    }
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(a), "h"(b));
+    return acc;
 }
 
-// 16 activations of type T (32 bytes) -> 8 float2
+// ---- per-dtype inner product of one 16-byte weight chunk (16 biased bytes u = q + 128) with 16 activations ----
+// fp16:  the bytes are PRMT-ed under the exponent byte 0x64 -> fp16(1024 + u) (no arithmetic), then FHFMA with
+//        the packed fp16 activations accumulates x * (1024 + u) exactly in fp32; the constant (1024 + 128) * sum(x)
+//        is removed once per row (XOffset below).  3 instructions per 2 weights, no int->float conversion at all.
+// bf16:  bf16 cannot hold 1024 + u, so bytes go through the fp32 mantissa trick (2^23 + u) - (2^23 + 128) = q and
+//        packed FFMA2 against fp32 activations.
 template <typename T>
-__device__ __forceinline__ void load_x16(const T* p, float2 (&out)[8])
-{
-    const uint4 a = *reinterpret_cast<const uint4*>(p);
-    const uint4 b = *reinterpret_cast<const uint4*>(p + 8);
-    const uint32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+struct XSlice;
+
+template <>
+struct XSlice<__half> {
+    uint32_t h2[8];  // 16 activations, packed fp16 pairs
+    float sum;       // their fp32 sum
+    __device__ __forceinline__ void load(const __half* p)
+    {
+        const uint4 a = *reinterpret_cast<const uint4*>(p);
+        const uint4 b = *reinterpret_cast<const uint4*>(p + 8);
+        h2[0] = a.x; h2[1] = a.y; h2[2] = a.z; h2[3] = a.w;
+        h2[4] = b.x; h2[5] = b.y; h2[6] = b.z; h2[7] = b.w;
+        float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if constexpr (sizeof(T) == 2 && DTypeOf<T>::value == EETQ_B200_F16) {
-            out[j] = __half22float2(*reinterpret_cast<const __half2*>(&raw[j]));
+        for (int j = 0; j < 8; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2[j]));
+            s += f.x + f.y;
         }
-        else {
-            out[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[j]));
+        sum = s;
+    }
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            h2[j] = 0u;
+        sum = 0.f;
+    }
+    __device__ __forceinline__ void resum()
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2[j]));
+            s += f.x + f.y;
+        }
+        sum = s;
+    }
+    __device__ __forceinline__ float sumsq() const
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2[j]));
+            s = fmaf(f.x, f.x, s);
+            s = fmaf(f.y, f.y, s);
+        }
+        return s;
+    }
+    // RMSNorm in place, HF Llama arithmetic: fp16( fp16(x_f32 * r) * w )
+    __device__ __forceinline__ void apply_norm(float r, const __half* nw)
+    {
+        const uint4 a = *reinterpret_cast<const uint4*>(nw);
+        const uint4 b = *reinterpret_cast<const uint4*>(nw + 8);
+        const uint32_t wr[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 f  = __half22float2(*reinterpret_cast<const __half2*>(&h2[j]));
+            const __half2 n = __floats2half2_rn(f.x * r, f.y * r);
+            const __half2 o = __hmul2(n, *reinterpret_cast<const __half2*>(&wr[j]));
+            h2[j]           = *reinterpret_cast<const uint32_t*>(&o);
+        }
+        resum();
+    }
+    // x = fp16( fp16(silu(g)) * u )  (HF: act_fn(gate_proj(x)) * up_proj(x) in fp16)
+    __device__ __forceinline__ void load_silu_mul(const __half* g, const __half* u)
+    {
+        const uint4 ga = *reinterpret_cast<const uint4*>(g), gb = *reinterpret_cast<const uint4*>(g + 8);
+        const uint4 ua = *reinterpret_cast<const uint4*>(u), ub = *reinterpret_cast<const uint4*>(u + 8);
+        const uint32_t gr[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const uint32_t ur[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 f  = __half22float2(*reinterpret_cast<const __half2*>(&gr[j]));
+            const __half2 a = __floats2half2_rn(f.x / (1.f + __expf(-f.x)), f.y / (1.f + __expf(-f.y)));
+            const __half2 o = __hmul2(a, *reinterpret_cast<const __half2*>(&ur[j]));
+            h2[j]           = *reinterpret_cast<const uint32_t*>(&o);
+        }
+        resum();
+    }
+    // acc += sum_j x_j * (1024 + u_j)
+    __device__ __forceinline__ void dot(const uint4& wv, float& acc) const
+    {
+        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t p01 = __byte_perm(words[q], 0x64646464u, 0x5140);
+            const uint32_t p23 = __byte_perm(words[q], 0x64646464u, 0x5342);
+            acc = fhfma(uint16_t(p01 & 0xffffu), uint16_t(h2[2 * q] & 0xffffu), acc);
+            acc = fhfma(uint16_t(p01 >> 16), uint16_t(h2[2 * q] >> 16), acc);
+            acc = fhfma(uint16_t(p23 & 0xffffu), uint16_t(h2[2 * q + 1] & 0xffffu), acc);
+            acc = fhfma(uint16_t(p23 >> 16), uint16_t(h2[2 * q + 1] >> 16), acc);
         }
     }
-}
+    static constexpr float kOffset = 1152.f;  // 1024 (exponent trick) + 128 (storage bias)
+};
+
+template <>
+struct XSlice<__nv_bfloat16> {
+    float2 f2[8];
+    float sum;  // unused (offset already removed per element)
+    __device__ __forceinline__ void load(const __nv_bfloat16* p)
+    {
+        const uint4 a = *reinterpret_cast<const uint4*>(p);
+        const uint4 b = *reinterpret_cast<const uint4*>(p + 8);
+        const uint32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            f2[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[j]));
+        sum = 0.f;
+    }
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            f2[j] = make_float2(0.f, 0.f);
+        sum = 0.f;
+    }
+    __device__ __forceinline__ float sumsq() const
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s = fmaf(f2[j].x, f2[j].x, s);
+            s = fmaf(f2[j].y, f2[j].y, s);
+        }
+        return s;
+    }
+    static __device__ __forceinline__ float rb(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+    __device__ __forceinline__ void apply_norm(float r, const __nv_bfloat16* nw)
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            f2[j].x = rb(rb(f2[j].x * r) * __bfloat162float(nw[2 * j]));
+            f2[j].y = rb(rb(f2[j].y * r) * __bfloat162float(nw[2 * j + 1]));
+        }
+    }
+    __device__ __forceinline__ void load_silu_mul(const __nv_bfloat16* g, const __nv_bfloat16* u)
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float g0 = __bfloat162float(g[2 * j]), g1 = __bfloat162float(g[2 * j + 1]);
+            f2[j].x = rb(rb(g0 / (1.f + __expf(-g0))) * __bfloat162float(u[2 * j]));
+            f2[j].y = rb(rb(g1 / (1.f + __expf(-g1))) * __bfloat162float(u[2 * j + 1]));
+        }
+        sum = 0.f;
+    }
+    __device__ __forceinline__ void dot(const uint4& wv, float& acc) const
+    {
+        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+        float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 lo, hi;
+            lo.x = __uint_as_float(__byte_perm(words[q], 0x4B000000u, 0x7650)) - 8388736.f;
+            lo.y = __uint_as_float(__byte_perm(words[q], 0x4B000000u, 0x7651)) - 8388736.f;
+            hi.x = __uint_as_float(__byte_perm(words[q], 0x4B000000u, 0x7652)) - 8388736.f;
+            hi.y = __uint_as_float(__byte_perm(words[q], 0x4B000000u, 0x7653)) - 8388736.f;
+            a2   = ffma2(lo, f2[2 * q], a2);
+            a2   = ffma2(hi, f2[2 * q + 1], a2);
+        }
+        acc += a2.x + a2.y;
+    }
+    static constexpr float kOffset = 0.f;
+};
 
 // Sum v[r] over the 32 lanes for all R rows with a transposing butterfly.  On return every lane holds,
 // in v[0], the warp total of row (lane >> (5 - log2 R)).
@@ -125,11 +270,27 @@ struct Log2<8> {
 // dynamic smem: partial[row][m][warp] fp32
 extern __shared__ float gemv_partial[];
 
-template <typename T, int M, int KITERS, int R, bool XREG, int CVT>
-__global__ void __launch_bounds__(kThreads, (XREG && M * KITERS <= 2) ? 2 : 1)
-    w8a16_gemv_kernel(const T* __restrict__ x, int64_t ldx, const int8_t* __restrict__ w, const T* __restrict__ scales,
-                      const T* __restrict__ bias, T* __restrict__ y, int64_t ldy, int N, int K, int max_rows)
+constexpr __host__ __device__ int min_ctas(int M, int KITERS, bool XREG) { return (XREG && M * KITERS <= 4) ? 2 : 1; }
+
+// Optional fusions around the GEMV (decode-side glue folded into the hot kernel; all pointers may be null):
+//   xmode GEMV_X_RMSNORM : the activation is RMS-normalised on load (x is the residual stream, norm_weight [K])
+//   xmode GEMV_X_SILU_MUL: the activation is silu(x[:, :K]) * x[:, K:2K]   (x is the fused gate|up output, ldx >= 2K)
+//   residual             : y = fp16(acc * s [+ bias]) + residual   (fp16 add, like `hidden = residual + o_proj(..)`)
+template <typename T>
+struct GemvFuse {
+    const T* norm_weight;
+    const T* residual;
+    int64_t ldr;
+    float eps;
+    int xmode;
+};
+
+template <typename T, int M, int KITERS, int R, bool XREG>
+__global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
+    w8a16_gemv_kernel(const T* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ w, const T* __restrict__ scales,
+                      const T* __restrict__ bias, T* __restrict__ y, int64_t ldy, int N, int K, const GemvFuse<T> fuse)
 {
+    __shared__ float red_smem[M][kWarps];
     const int tid     = threadIdx.x;
     const int lane    = tid & 31;
     const int warp    = tid >> 5;
@@ -141,11 +302,19 @@ __global__ void __launch_bounds__(kThreads, (XREG && M * KITERS <= 2) ? 2 : 1)
     const int nrows     = row_end - row_begin;
     const int ngroups   = (nrows + R - 1) / R;
 
-    // number of K-chunk iterations: compile-time for XREG, run-time otherwise
-    const int kiters = XREG ? KITERS : (nchunks + kThreads - 1) / kThreads;
-
     // let the next kernel in the stream start its own prologue (no-op without PDL)
     pdl_launch_dependents();
+
+    // warp butterfly + per-warp partial to smem for the R rows of group g
+    auto reduce_store = [&](float (&acc)[M][R], int g) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const float tot = warp_reduce_rows<R>(acc[m], lane);
+            const int rid   = lane >> (5 - Log2<R>::v);
+            if ((lane & ((32 >> Log2<R>::v) - 1)) == 0)
+                gemv_partial[((g * R + rid) * M + m) * kWarps + warp] = tot;
+        }
+    };
 
     if constexpr (XREG) {
         // ------------------------------------------------------------------ register-resident activations
@@ -168,73 +337,94 @@ __global__ void __launch_bounds__(kThreads, (XREG && M * KITERS <= 2) ? 2 : 1)
         // weights do not depend on the previous kernel: start streaming before the dependency wait
         if (ngroups > 0)
             load_group(wb[0], 0);
+        if (ngroups > 1)
+            load_group(wb[1], 1);
         pdl_wait_prior_grids();
 
-        float2 xs[M][KITERS][8];
+        XSlice<T> xs[M][KITERS];
+        float xoff[M];
 #pragma unroll
         for (int m = 0; m < M; ++m)
 #pragma unroll
             for (int i = 0; i < KITERS; ++i) {
                 const int c = tid + i * kThreads;
-                if (c < nchunks) {
-                    load_x16<T>(x + int64_t(m) * ldx + int64_t(c) * 16, xs[m][i]);
-                }
-                else {
+                if (c >= nchunks)
+                    xs[m][i].zero();
+                else if (fuse.xmode == GEMV_X_SILU_MUL)
+                    xs[m][i].load_silu_mul(x + int64_t(m) * ldx + int64_t(c) * 16, x + int64_t(m) * ldx + K + int64_t(c) * 16);
+                else
+                    xs[m][i].load(x + int64_t(m) * ldx + int64_t(c) * 16);
+            }
+        if (fuse.xmode == GEMV_X_RMSNORM) {
+            // every CTA holds the whole activation row across its threads: block-reduce sum(x^2), normalise in registers
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        xs[m][i][j] = make_float2(0.f, 0.f);
+            for (int m = 0; m < M; ++m) {
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < KITERS; ++i)
+                    ss += xs[m][i].sumsq();
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1)
+                    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (lane == 0)
+                    red_smem[m][warp] = ss;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                float tot = 0.f;
+#pragma unroll
+                for (int wi = 0; wi < kWarps; ++wi)
+                    tot += red_smem[m][wi];
+                const float r = rsqrtf(tot / float(K) + fuse.eps);
+#pragma unroll
+                for (int i = 0; i < KITERS; ++i) {
+                    const int c = tid + i * kThreads;
+                    if (c < nchunks)
+                        xs[m][i].apply_norm(r, fuse.norm_weight + int64_t(c) * 16);
                 }
             }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            float so = 0.f;
+#pragma unroll
+            for (int i = 0; i < KITERS; ++i)
+                so += xs[m][i].sum;
+            xoff[m] = -XSlice<T>::kOffset * so;
+        }
 
         auto compute_group = [&](uint4 (&buf)[R][KITERS], int g) {
             float acc[M][R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float2 a2[M];
 #pragma unroll
-                for (int m = 0; m < M; ++m)
-                    a2[m] = make_float2(0.f, 0.f);
+                for (int m = 0; m < M; ++m) {
+                    float a = xoff[m];
 #pragma unroll
-                for (int i = 0; i < KITERS; ++i) {
-                    const uint32_t words[4] = {buf[r][i].x, buf[r][i].y, buf[r][i].z, buf[r][i].w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float2 lo, hi;
-                        cvt4<CVT>(words[q], lo, hi);
-#pragma unroll
-                        for (int m = 0; m < M; ++m) {
-                            a2[m] = ffma2(lo, xs[m][i][2 * q], a2[m]);
-                            a2[m] = ffma2(hi, xs[m][i][2 * q + 1], a2[m]);
-                        }
-                    }
+                    for (int i = 0; i < KITERS; ++i)
+                        xs[m][i].dot(buf[r][i], a);
+                    acc[m][r] = a;
                 }
-#pragma unroll
-                for (int m = 0; m < M; ++m)
-                    acc[m][r] = a2[m].x + a2[m].y;
             }
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                const float tot = warp_reduce_rows<R>(acc[m], lane);
-                const int rid   = lane >> (5 - Log2<R>::v);
-                if ((lane & ((32 >> Log2<R>::v) - 1)) == 0)
-                    gemv_partial[((g * R + rid) * M + m) * kWarps + warp] = tot;
-            }
+            reduce_store(acc, g);
         };
 
         for (int g = 0; g < ngroups; g += 2) {
-            if (g + 1 < ngroups)
-                load_group(wb[1], g + 1);
             compute_group(wb[0], g);
+            if (g + 2 < ngroups)
+                load_group(wb[0], g + 2);
             if (g + 1 < ngroups) {
-                if (g + 2 < ngroups)
-                    load_group(wb[0], g + 2);
                 compute_group(wb[1], g + 1);
+                if (g + 3 < ngroups)
+                    load_group(wb[1], g + 3);
             }
         }
     }
     else {
-        // ------------------------------------------------------------------ activations re-read through L1
+        // ------------------------------------------------------------------ activations re-read through L1 (any M, any K)
         pdl_wait_prior_grids();
+        const int kiters = (nchunks + kThreads - 1) / kThreads;
         for (int g = 0; g < ngroups; ++g) {
             float acc[M][R];
 #pragma unroll
@@ -253,41 +443,20 @@ __global__ void __launch_bounds__(kThreads, (XREG && M * KITERS <= 2) ? 2 : 1)
                     buf[r]        = (row < row_end) ? ldg_stream_128(w + int64_t(row) * K + int64_t(c) * 16)
                                                     : make_uint4(0u, 0u, 0u, 0u);
                 }
-                float2 a2[M][R];
-#pragma unroll
-                for (int m = 0; m < M; ++m)
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        a2[m][r] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    float2 xv[8];
-                    load_x16<T>(x + int64_t(m) * ldx + int64_t(c) * 16, xv);
+                    XSlice<T> xv;
+                    xv.load(x + int64_t(m) * ldx + int64_t(c) * 16);
+                    const float off = -XSlice<T>::kOffset * xv.sum;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const uint32_t words[4] = {buf[r].x, buf[r].y, buf[r].z, buf[r].w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float2 lo, hi;
-                            cvt4<CVT>(words[q], lo, hi);
-                            a2[m][r] = ffma2(lo, xv[2 * q], a2[m][r]);
-                            a2[m][r] = ffma2(hi, xv[2 * q + 1], a2[m][r]);
-                        }
+                        float a = off;
+                        xv.dot(buf[r], a);
+                        acc[m][r] += a;
                     }
                 }
-#pragma unroll
-                for (int m = 0; m < M; ++m)
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        acc[m][r] += a2[m][r].x + a2[m][r].y;
             }
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                const float tot = warp_reduce_rows<R>(acc[m], lane);
-                const int rid   = lane >> (5 - Log2<R>::v);
-                if ((lane & ((32 >> Log2<R>::v) - 1)) == 0)
-                    gemv_partial[((g * R + rid) * M + m) * kWarps + warp] = tot;
-            }
+            reduce_store(acc, g);
         }
     }
 
@@ -304,23 +473,23 @@ __global__ void __launch_bounds__(kThreads, (XREG && M * KITERS <= 2) ? 2 : 1)
         float out   = s * to_float(scales[n]);
         if (bias != nullptr)
             out += to_float(bias[n]);
-        y[int64_t(m) * ldy + n] = from_float<T>(out);
+        T o = from_float<T>(out);
+        if (fuse.residual != nullptr)
+            o = from_float<T>(to_float(o) + to_float(fuse.residual[int64_t(m) * fuse.ldr + n]));
+        y[int64_t(m) * ldy + n] = o;
     }
-    (void)max_rows;
 }
 
-int g_gemv_cvt_mode = 1;  // 0 = I2F byte-select, 1 = PRMT magic (default); switchable for experiments
-
 template <typename T, int M, int KITERS, int R, bool XREG>
-int launch_variant(const T* x, int64_t ldx, const int8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N,
-                   int K, bool pdl, cudaStream_t stream)
+int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N,
+                   int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
     const DeviceInfo& di = device_info();
     if (!di.ok) {
         set_error("gemv: device query failed");
         return EETQ_B200_ECUDA;
     }
-    constexpr int kCtasPerSm = (XREG && M * KITERS <= 2) ? 2 : 1;
+    constexpr int kCtasPerSm = min_ctas(M, KITERS, XREG);
     constexpr int kMaxRows   = 96;  // rows per CTA bound (sizes the partial-sum buffer)
     int grid                 = di.sm_count * kCtasPerSm;
     // keep rows/CTA <= kMaxRows, and grid a multiple of the SM count
@@ -329,9 +498,8 @@ int launch_variant(const T* x, int64_t ldx, const int8_t* w, const T* scales, co
     if (grid > N)
         grid = N;
     const int max_rows = (N + grid - 1) / grid;
-    // partial buffer is indexed by padded group rows: round up to a multiple of R
-    const int padded  = ((max_rows + R - 1) / R) * R;
-    const size_t smem = size_t(padded) * M * kWarps * sizeof(float);
+    const int padded   = ((max_rows + R - 1) / R) * R;  // the partial buffer is indexed by padded group rows
+    const size_t smem  = size_t(padded) * M * kWarps * sizeof(float);
 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim          = dim3(unsigned(grid));
@@ -344,13 +512,8 @@ int launch_variant(const T* x, int64_t ldx, const int8_t* w, const T* scales, co
     cfg.attrs                                          = attr;
     cfg.numAttrs                                       = pdl ? 1 : 0;
 
-    cudaError_t e;
-    if (g_gemv_cvt_mode == 0)
-        e = cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG, 0>, x, ldx, w, scales, bias, y, ldy, N, K,
-                               max_rows);
-    else
-        e = cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG, 1>, x, ldx, w, scales, bias, y, ldy, N, K,
-                               max_rows);
+    const cudaError_t e =
+        cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG>, x, ldx, w, scales, bias, y, ldy, N, K, fuse);
     count_launch();
     if (e != cudaSuccess) {
         set_error("gemv launch failed: %s", cudaGetErrorString(e));
@@ -360,70 +523,68 @@ int launch_variant(const T* x, int64_t ldx, const int8_t* w, const T* scales, co
 }
 
 template <typename T, int M>
-int dispatch_k(const T* x, int64_t ldx, const int8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N,
-               int K, bool pdl, cudaStream_t stream)
+int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N, int K,
+               const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
     const int nchunks = K / 16;
     const int kiters  = (nchunks + kThreads - 1) / kThreads;
-    // register-resident activations when M * kiters * 16 fp32 fit comfortably (<= 64 registers)
-    if constexpr (M == 1) {
-        if (kiters == 1)
-            return launch_variant<T, 1, 1, 8, true>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        if (kiters == 2)
-            return launch_variant<T, 1, 2, 4, true>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        if (kiters == 3)
-            return launch_variant<T, 1, 3, 2, true>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        if (kiters == 4)
-            return launch_variant<T, 1, 4, 2, true>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
+    // register-resident activations while the slice stays small (fp16: 8 regs, bf16: 16 regs per 16 values)
+    constexpr int kMaxXregIters = (DTypeOf<T>::value == EETQ_B200_F16) ? 8 / M : 4 / M;
+#define EB_GEMV_CASE(KI, RS, RB)                                                                                        \
+    if (kiters == KI) {                                                                                                 \
+        if constexpr (KI <= kMaxXregIters)                                                                             \
+            return launch_variant<T, M, KI, (M <= 2 ? RS : RB), true>(x, ldx, w, scales, bias, y, ldy, N, K, fuse,     \
+                                                                      pdl, stream);                                     \
     }
-    if constexpr (M == 2) {
-        if (kiters == 1)
-            return launch_variant<T, 2, 1, 8, true>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        if (kiters == 2)
-            return launch_variant<T, 2, 2, 4, true>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
+    EB_GEMV_CASE(1, 8, 4)
+    EB_GEMV_CASE(2, 4, 2)
+    EB_GEMV_CASE(3, 2, 1)
+    EB_GEMV_CASE(4, 2, 1)
+#undef EB_GEMV_CASE
+    // general path: activations re-read through L1 (no fused prologue there)
+    if (fuse.xmode != GEMV_X_PLAIN) {
+        set_error("gemv: fused RMSNorm / SiLU-mul prologue needs M * ceil(K/4096) <= %d (got M=%d, K=%d)", M * kMaxXregIters, M, K);
+        return EETQ_B200_EINVAL;
     }
-    if constexpr (M == 3 || M == 4) {
-        if (kiters == 1)
-            return launch_variant<T, M, 1, 4, true>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-    }
-    // general path: activations re-read through L1
     constexpr int R = (M <= 2) ? 8 : 4;
-    return launch_variant<T, M, 1, R, false>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
+    return launch_variant<T, M, 1, R, false>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
 }
 
 template <typename T>
-int dispatch_m(const T* x, int64_t ldx, const int8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
-               int K, bool pdl, cudaStream_t stream)
+int dispatch_m(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
+               int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
     switch (M) {
-        case 1: return dispatch_k<T, 1>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        case 2: return dispatch_k<T, 2>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        case 3: return dispatch_k<T, 3>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        case 4: return dispatch_k<T, 4>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        case 5: return dispatch_k<T, 5>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        case 6: return dispatch_k<T, 6>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        case 7: return dispatch_k<T, 7>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
-        case 8: return dispatch_k<T, 8>(x, ldx, w, scales, bias, y, ldy, N, K, pdl, stream);
+        case 1: return dispatch_k<T, 1>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 2: return dispatch_k<T, 2>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 3: return dispatch_k<T, 3>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 4: return dispatch_k<T, 4>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 5: return dispatch_k<T, 5>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 6: return dispatch_k<T, 6>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 7: return dispatch_k<T, 7>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 8: return dispatch_k<T, 8>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
         default: set_error("gemv: M=%d out of range [1,%d]", M, EETQ_B200_GEMV_MAX_M); return EETQ_B200_EINVAL;
     }
 }
 
 }  // namespace
 
-extern "C" void eetq_b200_debug_set_gemv_cvt_mode(int mode) { g_gemv_cvt_mode = mode ? 1 : 0; }
-
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
-                int M, int64_t N, int64_t K, int dtype, bool pdl, cudaStream_t stream)
+                int M, int64_t N, int64_t K, int dtype, const GemvExtras& ex, bool pdl, cudaStream_t stream)
 {
-    if (dtype == EETQ_B200_F16)
-        return dispatch_m<__half>(static_cast<const __half*>(x), ldx, w, static_cast<const __half*>(scales),
-                                  static_cast<const __half*>(bias), static_cast<__half*>(y), ldy, M, int(N), int(K),
-                                  pdl, stream);
-    if (dtype == EETQ_B200_BF16)
-        return dispatch_m<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), ldx, w,
-                                         static_cast<const __nv_bfloat16*>(scales),
-                                         static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), ldy, M,
-                                         int(N), int(K), pdl, stream);
+    const uint8_t* wu = reinterpret_cast<const uint8_t*>(w);
+    if (dtype == EETQ_B200_F16) {
+        using T = __half;
+        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode};
+        return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
+                             static_cast<T*>(y), ldy, M, int(N), int(K), f, pdl, stream);
+    }
+    if (dtype == EETQ_B200_BF16) {
+        using T = __nv_bfloat16;
+        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode};
+        return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
+                             static_cast<T*>(y), ldy, M, int(N), int(K), f, pdl, stream);
+    }
     set_error("gemv: unsupported activation dtype %d", dtype);
     return EETQ_B200_EINVAL;
 }

@@ -5,7 +5,7 @@
 // and its 4-pass host layout transform
 //   preprocess_weights_for_mixed_gemm cutlass_preprocessors.cc:497-534
 // with HBM-bound kernels.  The target layout is NOT the reference's interleaved one but the
-// "b200 layout": plain int8, output-feature-major  w_b200[n*K + k] = q[k, n]  (DESIGN.md section 3),
+// "b200 layout": biased bytes, output-feature-major  w_b200[n*K + k] = uint8(q[k, n] + 128)  (DESIGN.md section 3),
 // which both the streaming GEMV (rows are contiguous K-vectors) and the tcgen05 GEMM (K-major UMMA
 // operand via a 2-D TMA box) consume directly, and whose column shards are contiguous byte ranges.
 //
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) quantize_tile_kernel(const T* __restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             q[j]            = quant_one(to_float(v[j]), s[j]);
-            tile[nl + j][k] = static_cast<int8_t>(q[j]);
+            tile[nl + j][k] = static_cast<int8_t>(q[j] ^ 0x80);  // stored biased: u = q + 128
         }
         if (q_kn != nullptr) {
             const uint32_t packed = (uint32_t(q[0]) & 0xffu) | ((uint32_t(q[1]) & 0xffu) << 8)
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) quantize_tile_kernel(const T* __restrict_
 // ---------------------------------------------------------------------------------------------------
 // byte-matrix transpose src[rows][cols] -> dst[cols][rows]   (pack: rows=K, cols=N; unpack: rows=N, cols=K)
 // ---------------------------------------------------------------------------------------------------
+// Every byte is XOR-ed with 0x80 on the way (signed int8 <-> biased uint8).
 __global__ void __launch_bounds__(256) transpose_bytes_kernel(const int8_t* __restrict__ src, int64_t rows, int64_t cols,
                                                               int8_t* __restrict__ dst)
 {
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) transpose_bytes_kernel(const int8_t* __re
         __align__(16) int8_t v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            v[j] = tile[rc + j][c];
+            v[j] = int8_t(tile[rc + j][c] ^ 0x80);
         *reinterpret_cast<uint4*>(dst + (c0 + c) * rows + r0 + rc) = *reinterpret_cast<const uint4*>(v);
     }
 }
@@ -176,11 +177,11 @@ __global__ void __launch_bounds__(256) from_ref_layout_kernel(const uint4* __res
     const int64_t pair   = (gi >> 3) / ktiles;
     const uint4 in       = w_ref[gi];
     uint4 out;
-    // out byte j = in byte p(j),  p = 2*(j&7) + (j>>3);  u - 128 == u ^ 0x80 as int8
-    out.x = __byte_perm(in.x, in.y, 0x6420) ^ 0x80808080u;
-    out.y = __byte_perm(in.z, in.w, 0x6420) ^ 0x80808080u;
-    out.z = __byte_perm(in.x, in.y, 0x7531) ^ 0x80808080u;
-    out.w = __byte_perm(in.z, in.w, 0x7531) ^ 0x80808080u;
+    // out byte j = in byte p(j),  p = 2*(j&7) + (j>>3);  both layouts store the biased byte u = q + 128
+    out.x = __byte_perm(in.x, in.y, 0x6420);
+    out.y = __byte_perm(in.z, in.w, 0x6420);
+    out.z = __byte_perm(in.x, in.y, 0x7531);
+    out.w = __byte_perm(in.z, in.w, 0x7531);
     const int64_t n = 2 * pair + c;
     *reinterpret_cast<uint4*>(q_b200 + n * K + 64 * kt + 16 * g) = out;
 }
@@ -200,10 +201,10 @@ __global__ void __launch_bounds__(256) to_ref_layout_kernel(const int8_t* __rest
     const uint4 in       = *reinterpret_cast<const uint4*>(q_b200 + n * K + 64 * kt + 16 * g);
     uint4 out;
     // out byte p = in byte j(p),  j = (p>>1) + 8*(p&1)
-    out.x = __byte_perm(in.x, in.z, 0x5140) ^ 0x80808080u;
-    out.y = __byte_perm(in.x, in.z, 0x7362) ^ 0x80808080u;
-    out.z = __byte_perm(in.y, in.w, 0x5140) ^ 0x80808080u;
-    out.w = __byte_perm(in.y, in.w, 0x7362) ^ 0x80808080u;
+    out.x = __byte_perm(in.x, in.z, 0x5140);
+    out.y = __byte_perm(in.x, in.z, 0x7362);
+    out.z = __byte_perm(in.y, in.w, 0x5140);
+    out.w = __byte_perm(in.y, in.w, 0x7362);
     w_ref[gi] = out;
 }
 

@@ -1,0 +1,376 @@
+"""Llama-family decode harness on top of the w8a16 kernels -- what bench.py measures (BASELINE.json: "decode
+tokens/sec Llama-2-7B w8a16 @1/2/4/8 B200").
+
+This is the caller either side of the hot path (SURVEY.md section 8 "next"), kept deliberately small:
+
+* ``LlamaSkeleton``      -- an ``nn.Module`` tree with the Hugging Face Llama sub-module names (random-init, there is no
+                            network for checkpoints) so that ``eet_quantize`` walks it exactly like it walks a HF model
+                            (/root/reference/python/eetq/utils/quantizer.py:40-61).  Its ``forward`` is a plain PyTorch
+                            implementation used as the numerical reference in tests.
+* ``W8A16LlamaDecoder``  -- takes the quantised model, fuses q|k|v and gate|up row-wise (trivial in the b200 layout:
+                            rows are output features), and runs single-token decode as ONE CUDA graph of native kernels:
+                            per layer 4 streaming GEMVs (RMSNorm / SiLU*up / residual fused into them), RoPE+KV-append
+                            and split-KV attention, chained with programmatic dependent launch so that the weight
+                            stream of kernel i+1 starts while kernel i drains.
+                            With ``world_size > 1`` every linear is column-sharded (rank r owns rows
+                            [r*N/P, (r+1)*N/P) of each fused weight -- a contiguous byte range) and the activations are
+                            all-gathered after each linear.
+
+The reference's own end-to-end path is HF ``generate`` over ``W8A16Linear`` modules
+(/root/reference/examples/models/llama_transformers_example.py:22-90); its attention side
+(/root/reference/python/eetq/modules/llama_modules.py) is outside the w8a16 hot path.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi
+from .modules.qlinear import W8A16Linear
+from .ops import w8_a16_gemm_bias
+
+__all__ = ["LlamaShape", "LlamaSkeleton", "W8A16LlamaDecoder", "LLAMA2_7B", "LLAMA2_13B"]
+
+
+@dataclass
+class LlamaShape:
+    hidden: int = 4096
+    inter: int = 11008
+    layers: int = 32
+    heads: int = 32
+    vocab: int = 32000
+    eps: float = 1e-5
+    theta: float = 10000.0
+    name: str = "llama-2-7b"
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+
+LLAMA2_7B = LlamaShape()
+LLAMA2_13B = LlamaShape(hidden=5120, inter=13824, layers=40, heads=40, name="llama-2-13b")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# skeleton with HF sub-module names
+# ---------------------------------------------------------------------------------------------------------------------
+class _RMSNorm(nn.Module):
+    def __init__(self, n, eps, device, dtype):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n, device=device, dtype=dtype), requires_grad=False)
+        self.eps = eps
+
+    def forward(self, x):
+        xf = x.float()
+        xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.eps)
+        return self.weight * xf.to(x.dtype)
+
+
+class _Attn(nn.Module):
+    def __init__(self, s: LlamaShape, device, dtype):
+        super().__init__()
+        H = s.hidden
+        self.q_proj = nn.Linear(H, H, bias=False, device=device, dtype=dtype)
+        self.k_proj = nn.Linear(H, H, bias=False, device=device, dtype=dtype)
+        self.v_proj = nn.Linear(H, H, bias=False, device=device, dtype=dtype)
+        self.o_proj = nn.Linear(H, H, bias=False, device=device, dtype=dtype)
+
+
+class _MLP(nn.Module):
+    def __init__(self, s: LlamaShape, device, dtype):
+        super().__init__()
+        self.gate_proj = nn.Linear(s.hidden, s.inter, bias=False, device=device, dtype=dtype)
+        self.up_proj = nn.Linear(s.hidden, s.inter, bias=False, device=device, dtype=dtype)
+        self.down_proj = nn.Linear(s.inter, s.hidden, bias=False, device=device, dtype=dtype)
+
+
+class _Layer(nn.Module):
+    def __init__(self, s: LlamaShape, device, dtype):
+        super().__init__()
+        self.self_attn = _Attn(s, device, dtype)
+        self.mlp = _MLP(s, device, dtype)
+        self.input_layernorm = _RMSNorm(s.hidden, s.eps, device, dtype)
+        self.post_attention_layernorm = _RMSNorm(s.hidden, s.eps, device, dtype)
+
+
+class _Model(nn.Module):
+    def __init__(self, s: LlamaShape, device, dtype):
+        super().__init__()
+        self.embed_tokens = nn.Embedding(s.vocab, s.hidden, device=device, dtype=dtype)
+        self.layers = nn.ModuleList([_Layer(s, device, dtype) for _ in range(s.layers)])
+        self.norm = _RMSNorm(s.hidden, s.eps, device, dtype)
+
+
+def rope_tables(s: LlamaShape, max_pos: int, device, dtype):
+    """cos/sin [max_pos, D/2] exactly as HF LlamaRotaryEmbedding builds them (fp32 math, cast to the model dtype)."""
+    D = s.head_dim
+    inv_freq = 1.0 / (s.theta ** (torch.arange(0, D, 2, dtype=torch.float32, device=device) / D))
+    freqs = torch.arange(max_pos, dtype=torch.float32, device=device)[:, None] * inv_freq[None, :]
+    return freqs.cos().to(dtype).contiguous(), freqs.sin().to(dtype).contiguous()
+
+
+def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """x [T, heads, D]; cos/sin [T, D/2]; HF rotate_half convention, evaluated in the model dtype."""
+    half = x.shape[-1] // 2
+    c = torch.cat([cos, cos], -1)[:, None, :]
+    s = torch.cat([sin, sin], -1)[:, None, :]
+    rot = torch.cat([-x[..., half:], x[..., :half]], -1)
+    return x * c + rot * s
+
+
+class LlamaSkeleton(nn.Module):
+    """Random-init Llama with HF sub-module names (``model.layers.N.self_attn.q_proj`` ... ``lm_head``)."""
+
+    def __init__(self, shape: LlamaShape, device="cuda", dtype=torch.float16, seed: int = 1000, std: float = 0.02):
+        super().__init__()
+        self.shape = shape
+        self.model = _Model(shape, device, dtype)
+        self.lm_head = nn.Linear(shape.hidden, shape.vocab, bias=False, device=device, dtype=dtype)
+        g = torch.Generator(device=device).manual_seed(seed)
+        with torch.no_grad():
+            for p in self.parameters():
+                if p.dim() >= 2:  # linears + embedding: N(0, 0.02^2) like the Llama init
+                    p.copy_((torch.randn(p.shape, generator=g, device=device, dtype=torch.float32) * std).to(dtype))
+
+    @torch.no_grad()
+    def forward(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Plain PyTorch causal forward for a 1-D token tensor; returns logits [T, vocab].  Works before and after
+        eet_quantize (the linears are called as modules)."""
+        s = self.shape
+        T = tokens.shape[0]
+        x = self.model.embed_tokens(tokens)
+        cos, sin = rope_tables(s, T, x.device, x.dtype)
+        for layer in self.model.layers:
+            h = layer.input_layernorm(x)
+            a = layer.self_attn
+            q = a.q_proj(h).view(T, s.heads, s.head_dim)
+            k = a.k_proj(h).view(T, s.heads, s.head_dim)
+            v = a.v_proj(h).view(T, s.heads, s.head_dim)
+            q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
+            o = F.scaled_dot_product_attention(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), is_causal=True)
+            x = x + a.o_proj(o.transpose(0, 1).reshape(T, s.hidden))
+            h = layer.post_attention_layernorm(x)
+            m = layer.mlp
+            x = x + m.down_proj(F.silu(m.gate_proj(h)) * m.up_proj(h))
+        return self.lm_head(self.model.norm(x))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# decoder
+# ---------------------------------------------------------------------------------------------------------------------
+def _vp(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _rows(lin: W8A16Linear) -> torch.Tensor:
+    """b200 bytes of a quantised linear as a [N, K] uint8 matrix (row n = output feature n)."""
+    K, N = lin.qweight.shape
+    return lin.qweight.view(torch.uint8).view(N, K)
+
+
+class _ShardedLinear:
+    """Rows [r*N/P, (r+1)*N/P) of a (possibly fused) quantised linear on this rank."""
+
+    def __init__(self, lins: List[W8A16Linear], rank: int, world: int):
+        rows = torch.cat([_rows(l) for l in lins], 0)
+        scales = torch.cat([l.weight_scales for l in lins], 0)
+        N, K = rows.shape
+        assert N % (64 * world) == 0, f"N={N} cannot be column-sharded {world}-way in multiples of 64"
+        self.N, self.K = N, K
+        self.n_local = N // world
+        self.n_begin = rank * self.n_local
+        sl = slice(self.n_begin, self.n_begin + self.n_local)
+        self.w = rows[sl].contiguous().view(torch.int8).view(K, self.n_local)  # nominal [K, N_local] like the reference
+        self.scales = scales[sl].contiguous()
+
+
+class W8A16LlamaDecoder:
+    SPLITS = 8  # KV splits of the decode attention
+
+    def __init__(self, model: nn.Module, shape: LlamaShape, max_ctx: int = 1280, pdl: bool = True, rank: int = 0, world_size: int = 1,
+                 group=None):
+        self.shape, self.max_ctx, self.pdl = shape, max_ctx, bool(pdl)
+        self.rank, self.world, self.group = rank, world_size, group
+        m = model.model
+        dev = m.embed_tokens.weight.device
+        self.device = dev
+        dt = torch.float16
+        self.embed = m.embed_tokens.weight.detach()
+        self.lm_head_w = model.lm_head.weight.detach()  # fp16 [V, H], not quantised (quantizer.py:40 excludes lm_head)
+        self.norm_w = m.norm.weight.detach()
+        self.layers = []
+        for layer in m.layers:
+            a, p = layer.self_attn, layer.mlp
+            for lin in (a.q_proj, a.k_proj, a.v_proj, a.o_proj, p.gate_proj, p.up_proj, p.down_proj):
+                assert isinstance(lin, W8A16Linear), "run eet_quantize(model) first"
+            self.layers.append(dict(
+                qkv=_ShardedLinear([a.q_proj, a.k_proj, a.v_proj], rank, world_size),
+                o=_ShardedLinear([a.o_proj], rank, world_size),
+                gu=_ShardedLinear([p.gate_proj, p.up_proj], rank, world_size),
+                down=_ShardedLinear([p.down_proj], rank, world_size),
+                ln1=layer.input_layernorm.weight.detach(), ln2=layer.post_attention_layernorm.weight.detach()))
+        H, I, L = shape.hidden, shape.inter, shape.layers
+        self.cos, self.sin = rope_tables(shape, max_ctx, dev, dt)
+        self.kcache = torch.zeros(L, max_ctx, H, dtype=dt, device=dev)
+        self.vcache = torch.zeros(L, max_ctx, H, dtype=dt, device=dev)
+        # decode-step buffers (device resident; the graph reads/writes these)
+        self.token = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.x = torch.zeros(H, dtype=dt, device=dev)
+        self.x2 = torch.zeros(H, dtype=dt, device=dev)
+        self.qkv = torch.zeros(3 * H, dtype=dt, device=dev)
+        self.attn = torch.zeros(H, dtype=dt, device=dev)
+        self.gu = torch.zeros(2 * I, dtype=dt, device=dev)
+        self.xn = torch.zeros(1, H, dtype=dt, device=dev)
+        self.logits = torch.zeros(1, shape.vocab, dtype=dt, device=dev)
+        self.partial = torch.zeros(shape.heads * self.SPLITS * (shape.head_dim + 2), dtype=torch.float32, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        self._L = _cabi.lib()
+
+    # ------------------------------------------------------------------------------------------------- construction
+    @classmethod
+    def from_model(cls, model: nn.Module, **kw) -> "W8A16LlamaDecoder":
+        return cls(model, model.shape, **kw)
+
+    # ------------------------------------------------------------------------------------------------- helpers
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _gemv(self, x, ldx, lin: _ShardedLinear, y_full, *, norm_w=None, xmode=0, residual_full=None):
+        """y_full[n_begin : n_begin + n_local] = fused GEMV over this rank's rows; then all-gather if sharded."""
+        off = lin.n_begin
+        y = y_full[off:off + lin.n_local]
+        res = None if residual_full is None else residual_full[off:off + lin.n_local]
+        rc = self._L.eetq_b200_w8a16_gemv_fused(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), None, _vp(norm_w), float(self.shape.eps),
+                                                xmode, _vp(res), lin.N, _vp(y), lin.N, 1, lin.n_local, lin.K, _cabi.F16,
+                                                1 if self.pdl else 0, self._stream())
+        _cabi.check(rc, "eetq_b200_w8a16_gemv_fused")
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_gather_into_tensor(y_full[:lin.N], y, group=self.group)
+
+    # ------------------------------------------------------------------------------------------------- one decode step
+    def _enqueue_step(self):
+        """Enqueue one token's worth of kernels on the current stream (captured once into a CUDA graph)."""
+        s, L, pdl = self.shape, self._L, 1 if self.pdl else 0
+        H, I, D = s.hidden, s.inter, s.head_dim
+        st = self._stream
+        _cabi.check(L.eetq_b200_decode_embed(_vp(self.embed), _vp(self.token), _vp(self.x), H, pdl, st()), "decode_embed")
+        for li, w in enumerate(self.layers):
+            self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1)
+            _cabi.check(L.eetq_b200_decode_rope_append(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
+                                                       _vp(self.vcache[li]), H, D, pdl, st()), "decode_rope_append")
+            _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.kcache[li]), _vp(self.vcache[li]), _vp(self.pos),
+                                                     _vp(self.partial), _vp(self.attn), H, D, self.SPLITS, self.max_ctx, pdl, st()),
+                        "decode_attention")
+            # x2 = x + o_proj(attn); x = x2 + down(silu(gate) * up)   (ping-pong so no kernel reads what it writes)
+            self._gemv(self.attn, H, w["o"], self.x2, residual_full=self.x)
+            self._gemv(self.x2, H, w["gu"], self.gu, norm_w=w["ln2"], xmode=1)
+            self._gemv(self.gu, 2 * I, w["down"], self.x, xmode=2, residual_full=self.x2)
+        _cabi.check(L.eetq_b200_decode_rmsnorm(_vp(self.x), _vp(self.norm_w), _vp(self.xn), 1, H, float(s.eps), pdl, st()), "decode_rmsnorm")
+        torch.matmul(self.xn, self.lm_head_w.t(), out=self.logits)       # fp16 lm_head (library GEMV; not quantised)
+        self.token.copy_(torch.argmax(self.logits, dim=-1))               # greedy
+        self.pos.add_(1)
+
+    def capture(self):
+        """Warm up (lazy module loads, cuBLAS handles) and capture the decode step into a CUDA graph."""
+        saved_pos, saved_tok = self.pos.clone(), self.token.clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._enqueue_step()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.pos.copy_(saved_pos)
+        self.token.copy_(saved_tok)
+        before = _cabi.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue_step()
+        self.launches_per_step = _cabi.launch_count() - before
+        torch.cuda.synchronize(self.device)
+        self.pos.copy_(saved_pos)
+        self.token.copy_(saved_tok)
+
+    def step(self):
+        """Advance one token entirely on the device (token/pos buffers are updated by the graph)."""
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+
+    def step_host(self, token_host: torch.Tensor, out_host: torch.Tensor):
+        """Public end-to-end call: token id in PINNED host memory -> next token id in pinned host memory
+        (H2D copy, one decode step, D2H copy, synchronise)."""
+        self.token.copy_(token_host, non_blocking=True)
+        self.step()
+        out_host.copy_(self.token, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host
+
+    # ------------------------------------------------------------------------------------------------- prefill
+    @torch.no_grad()
+    def prefill(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Process a prompt [T] with the batched (tcgen05) kernels, fill the KV cache, return the first new token."""
+        s = self.shape
+        T, H = tokens.shape[0], s.hidden
+        assert T < self.max_ctx
+        x = self.embed[tokens]
+        cos, sin = self.cos[:T], self.sin[:T]
+
+        def lin(inp, l: _ShardedLinear):
+            y = w8_a16_gemm_bias(inp, l.w, l.scales, None)
+            if self.world > 1:
+                import torch.distributed as dist
+
+                parts = [torch.empty_like(y) for _ in range(self.world)]
+                dist.all_gather(parts, y, group=self.group)
+                y = torch.cat(parts, -1)
+            return y
+
+        def rms(v, w):
+            vf = v.float()
+            return w * (vf * torch.rsqrt(vf.pow(2).mean(-1, keepdim=True) + s.eps)).to(v.dtype)
+
+        for li, w in enumerate(self.layers):
+            qkv = lin(rms(x, w["ln1"]), w["qkv"])
+            q = apply_rope(qkv[:, :H].reshape(T, s.heads, s.head_dim), cos, sin)
+            k = apply_rope(qkv[:, H:2 * H].reshape(T, s.heads, s.head_dim), cos, sin)
+            v = qkv[:, 2 * H:].reshape(T, s.heads, s.head_dim)
+            self.kcache[li, :T] = k.reshape(T, H)
+            self.vcache[li, :T] = v.reshape(T, H)
+            o = F.scaled_dot_product_attention(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), is_causal=True)
+            x = x + lin(o.transpose(0, 1).reshape(T, H), w["o"])
+            gu = lin(rms(x, w["ln2"]), w["gu"])
+            x = x + lin(F.silu(gu[:, :s.inter]) * gu[:, s.inter:], w["down"])
+        logits = torch.matmul(rms(x[-1:], self.norm_w), self.lm_head_w.t())
+        self.token.copy_(torch.argmax(logits, dim=-1))
+        self.pos.fill_(T)
+        return self.token.clone()
+
+    def set_context(self, ctx_len: int, token: int = 1):
+        """Pretend `ctx_len` tokens are already cached (cache content stays as is) -- for benchmarks/tests."""
+        self.pos.fill_(ctx_len)
+        self.token.fill_(token)
+
+    @torch.no_grad()
+    def generate(self, prompt: torch.Tensor, max_new_tokens: int) -> List[int]:
+        out = [int(self.prefill(prompt).item())]
+        for _ in range(max_new_tokens - 1):
+            self.step()
+            out.append(int(self.token.item()))
+        return out
+
+    # ------------------------------------------------------------------------------------------------- accounting
+    def weight_bytes_per_token(self) -> int:
+        """int8 weight bytes THIS rank streams per decoded token (quantised linears only)."""
+        return sum(l.n_local * l.K for w in self.layers for l in (w["qkv"], w["o"], w["gu"], w["down"]))

@@ -18,8 +18,9 @@
  *     std::runtime_error / asserts: csrc/utils/cuda_utils.h:29-51, weightOnlyBatchedGemv/kernelLauncher.cu:124-127).
  *   - Logical shapes follow the reference: x [M,K] row-major activations, logical weight Wq int8 [K,N]
  *     (K = in_features, N = out_features), scales [N], y [M,N] row-major.
- *   - "b200 layout" (DESIGN.md section 3): the K*N weight bytes stored output-feature-major,
- *     w_b200[n*K + k] = Wq[k, n], plain signed int8.  It replaces the reference's sm80 interleaved
+ *   - "b200 layout" (DESIGN.md section 3): the K*N weight bytes stored output-feature-major and biased,
+ *     w_b200[n*K + k] = uint8(Wq[k, n] + 128) (the reference biases by +128 too, cutlass_preprocessors.cc:337-341;
+ *     the bias lets the kernels build fp16(1024 + u) with one PRMT).  It replaces the reference's sm80 interleaved
  *     layout (cutlass_preprocessors.cc:497-534).  Requires K % 64 == 0 and N % 64 == 0 exactly like the
  *     reference (cutlass_preprocessors.cc:230,455; fpA_intB_gemm_template.h:139-142).
  */
@@ -108,8 +109,10 @@ int eetq_b200_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t*
  *   x [M,K] dtype, row stride ldx elements (ldx >= K; pass K for contiguous)
  *   w_b200 K*N int8 in b200 layout;  scales [N] dtype;  bias [N] dtype or NULL
  *   y [M,N] dtype, row stride ldy elements
- *   workspace: eetq_b200_workspace_bytes(M,N,K) bytes, ZERO-INITIALISED ONCE by the caller (the kernels
- *   leave it zeroed); may be NULL when that function returns 0.  One workspace must not be shared by
+ *   workspace: at least eetq_b200_workspace_bytes(M,N,K) bytes, ZERO-INITIALISED ONCE by the caller; its first
+ *   4 KiB hold split-K tile counters that every call leaves at zero, the rest is scratch, so ONE buffer sized for
+ *   the largest call can be reused by calls of any shape.  May be NULL when that function returns 0 (if it is
+ *   NULL or too small otherwise, the call still succeeds without split-K).  One workspace must not be shared by
  *   calls that can run concurrently.
  * ------------------------------------------------------------------------------------------- */
 size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K);
@@ -127,6 +130,33 @@ int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, co
 int eetq_b200_w8a16_gemm_host(const void* x_host, void* x_dev, const int8_t* w_b200, const void* scales,
                               const void* bias, void* y_dev, void* y_host, int64_t M, int64_t N, int64_t K, int dtype,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Decode-side extensions (SURVEY.md section 8 "next", rank 2 and 4) -- NOT part of the reference's w8a16 boundary.
+ * They exist so the headline metric (Llama-2-7B decode tokens/s) is bounded by the weight stream, not by
+ * framework-op launches.  fp16 only, single token.  `pdl` != 0 launches with programmatic dependent launch.
+ *
+ * eetq_b200_w8a16_gemv_fused: the decode GEMV (M <= 8) with glue folded in:
+ *   xmode 0: plain;  1: x := RMSNorm(x; norm_weight, eps) on load (HF LlamaRMSNorm arithmetic; replaces the
+ *   reference's separate generalT5LayerNorm kernel, csrc/layernorm_kernels/layernorm.cu:25-51);
+ *   2: x := silu(x[:, :K]) * x[:, K:2K] (fused gate|up activation; ldx >= 2K);
+ *   residual != NULL: y = dtype(acc * s [+ bias]) + residual  (the reference never wired FT's residual epilogues,
+ *   fpA_intB_gemm_template.h:492-537).
+ * ------------------------------------------------------------------------------------------- */
+int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
+                               const void* norm_weight, float eps, int xmode, const void* residual, int64_t ldr, void* y,
+                               int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, int pdl, void* stream);
+/* x[0:H] = table[*token] */
+int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, int pdl, void* stream);
+/* y = RMSNorm(x) * w over M rows of H */
+int eetq_b200_decode_rmsnorm(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, int pdl, void* stream);
+/* RoPE (rotate_half convention; behaviour of rotary_embedding_neox, csrc/embedding_kernels/pos_encoding_kernels.cu:12-53)
+ * on q,k of qkv = [q | k | v] (3*H) at position *pos, q rotated in place, k,v appended to the caches [max_ctx][H] */
+int eetq_b200_decode_rope_append(void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
+                                 void* vcache, int64_t H, int64_t D, int pdl, void* stream);
+/* one-token attention over cache positions [0, *pos]; head_dim 128; partial = H/D * splits * 130 floats scratch */
+int eetq_b200_decode_attention(const void* q, const void* kcache, const void* vcache, const void* pos_i32, void* partial,
+                               void* out, int64_t H, int64_t D, int64_t splits, int64_t max_ctx, int pdl, void* stream);
 
 /* number of kernels this library has launched on this process so far (bench.py's gpu_launches) */
 uint64_t eetq_b200_launch_count(void);

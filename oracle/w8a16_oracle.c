@@ -117,14 +117,14 @@ int oracle_ref_layout_inv(const uint8_t* in, size_t K, size_t N, int8_t* q_kn)
 
 /* ---------------------------------------------------------------------------------------------
  * The layout THIS repository's kernels consume ("b200 layout"):
- * plain int8, output-feature-major:  out[n*K + k] = q[k, n]   (i.e. nn.Linear.weight order).
+ * biased bytes, output-feature-major:  out[n*K + k] = uint8(q[k, n] + 128)   (nn.Linear.weight order).
  * Not a reference function -- it is restated here so tests can check the CUDA packer bit-for-bit.
  * ------------------------------------------------------------------------------------------- */
-void oracle_b200_layout(const int8_t* q_kn, size_t K, size_t N, int8_t* out_nk)
+void oracle_b200_layout(const int8_t* q_kn, size_t K, size_t N, uint8_t* out_nk)
 {
     for (size_t n = 0; n < N; ++n)
         for (size_t k = 0; k < K; ++k)
-            out_nk[n * K + k] = q_kn[k * N + n];
+            out_nk[n * K + k] = (uint8_t)((int)q_kn[k * N + n] + 128);
 }
 
 /* ---------------------------------------------------------------------------------------------

@@ -47,7 +47,8 @@ def quantize(w_kn: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tens
     """
     assert w_kn.dtype in (torch.float16, torch.float32) and w_kn.dim() in (2, 3)
     wf = w_kn.float()
-    s32 = wf.abs().amax(dim=-2) * np.float32(1.0 / 128.0)
+    # std::max(acc, NaN) keeps acc (cutlass_preprocessors.cc:626): NaN entries do not contribute to the abs-max
+    s32 = torch.nan_to_num(wf.abs(), nan=0.0, posinf=float("inf")).amax(dim=-2) * np.float32(1.0 / 128.0)
     r = wf / s32.unsqueeze(-2)
     r = torch.where(r >= 0, torch.floor(r + 0.5), torch.ceil(r - 0.5))
     # round-half-away via floor(r+0.5) is exact here: |r| <= 128 so r+0.5 is representable in fp32
@@ -90,15 +91,18 @@ def ref_layout_inv(w_ref: torch.Tensor) -> torch.Tensor:
 # the layout our kernels consume -- restated so the CUDA packer can be checked
 # ------------------------------------------------------------------------------------------------
 def b200_layout(q_kn: torch.Tensor) -> torch.Tensor:
-    """Row-major int8 ``[K, N]`` -> output-feature-major bytes ``[N][K]``, returned *shaped* ``[K, N]``
-    (the nominal shape the reference API uses for its processed tensor, fpA_intB_gemm_wrapper.cu:71)."""
+    """Row-major int8 ``[K, N]`` -> output-feature-major biased bytes ``out[n*K + k] = uint8(q[k, n] + 128)``,
+    returned as int8 *shaped* ``[K, N]`` (the nominal shape the reference API uses for its processed tensor,
+    fpA_intB_gemm_wrapper.cu:71)."""
     K, N = q_kn.shape
-    return q_kn.t().contiguous().view(K, N)
+    u = (q_kn.t().contiguous().to(torch.int16) + 128).to(torch.uint8)
+    return u.view(torch.int8).view(K, N)
 
 
 def b200_layout_inv(w_b200: torch.Tensor) -> torch.Tensor:
     K, N = w_b200.shape
-    return w_b200.contiguous().view(N, K).t().contiguous()
+    u = w_b200.contiguous().view(torch.uint8).view(N, K)
+    return (u.to(torch.int16) - 128).to(torch.int8).t().contiguous()
 
 
 # ------------------------------------------------------------------------------------------------

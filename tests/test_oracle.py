@@ -51,7 +51,7 @@ def test_b200_layout_roundtrip(oracle):
     q = torch.randint(-128, 128, (192, 128), dtype=torch.int8)
     w = oracle.b200_layout(q)
     assert w.shape == q.shape
-    assert torch.equal(w.view(128, 192), q.t())
+    assert torch.equal(w.view(torch.uint8).view(128, 192).to(torch.int16) - 128, q.t().to(torch.int16))
     assert torch.equal(oracle.b200_layout_inv(w), q)
 
 
@@ -83,6 +83,20 @@ def test_c_port_matches_torch_port(oracle, dtype):
         y1 = oracle.port_gemm_f16(x, q, s)
         y2 = oracle.gemm(x, q, s)
         assert oracle.norm_rel_err(y1, y2) <= 1e-3
+
+
+def test_nan_entries_are_ignored_by_absmax(oracle):
+    """std::max(acc, NaN) keeps acc in the reference (cutlass_preprocessors.cc:626); a NaN weight quantises to 127."""
+    w = oracle.synth_weight(64, 64, seed=6)
+    w[3, 2] = float("nan")
+    q, s, _ = oracle.quantize(w)
+    assert not torch.isnan(s).any() and q[3, 2] == 127
+    if oracle.ref_lib() is not None:
+        unp, _, sc = oracle.ref_quantize(w)
+        assert torch.equal(q, unp) and torch.equal(s.view(torch.int16), sc.view(torch.int16))
+    if oracle.port_lib() is not None:
+        q2, s2, _ = oracle.port_quantize(w)
+        assert torch.equal(q, q2) and torch.equal(s.view(torch.int16), s2.view(torch.int16))
 
 
 def test_oracle_3d_experts(oracle):

@@ -57,9 +57,8 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     lib = _cabi.lib()
-    lib.eetq_b200_debug_set_gemv_cvt_mode.argtypes = [ctypes.c_int]
     results = []
-    shapes = [(4096, 4096), (4096, 11008), (11008, 4096)]
+    shapes = [(4096, 4096), (4096, 12288), (4096, 22016), (11008, 4096)]
 
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_gemv.so")
     ref = ctypes.CDLL(ref_path) if os.path.exists(ref_path) else None
@@ -71,8 +70,7 @@ def main():
         sc = (torch.rand(N, device=dev) * 0.01).half()
         for M in ([1, 2, 4] if not args.quick else [1]):
             x = torch.randn(M, K, device=dev).half()
-            for mode, pdl in ((1, False), (0, False), (1, True)):
-                lib.eetq_b200_debug_set_gemv_cvt_mode(mode)
+            for mode, pdl in ((1, False), (1, True)):
                 flags = _cabi.FLAG_FORCE_GEMV | (_cabi.FLAG_PDL if pdl else 0)
                 fns = [(lambda w=w: w8_a16_gemm_bias(x, w, sc, None, flags=flags)) for w in ws]
                 med, best = time_graph(fns)
@@ -80,7 +78,6 @@ def main():
                          gbs=algo_bytes(M, N, K) / med / 1e3)
                 print(json.dumps(r), flush=True)
                 results.append(r)
-            lib.eetq_b200_debug_set_gemv_cvt_mode(1)
             if ref is not None:
                 y = torch.empty(M, N, device=dev, dtype=torch.float16)
                 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
