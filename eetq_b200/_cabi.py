@@ -44,8 +44,9 @@ SIGNATURES = {
                                             _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
     "eetq_b200_decode_embed": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "eetq_b200_decode_rmsnorm": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_int, _c_vp]),
-    "eetq_b200_decode_rope_append": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
-    "eetq_b200_decode_attention": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp]),
+    "eetq_b200_decode_attention_splits": (_c_i64, [_c_i64]),
+    "eetq_b200_decode_attention": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
+                                            _c_int, _c_vp]),
 }
 
 

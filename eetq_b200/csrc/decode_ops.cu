@@ -68,103 +68,129 @@ __global__ void __launch_bounds__(512) rmsnorm_kernel(const __half* __restrict__
         yr[i] = __hmul(__float2half_rn(__half2float(xr[i]) * r), w[i]);
 }
 
-// RoPE (HF "rotate_half" convention: pairs (i, i + D/2)) on q and k of one token, then append k, v to the cache.
-//   qkv   [3*H] = q | k | v   (q is rotated in place)
-//   cos/sin tables [max_pos][D/2] fp16 (HF computes them in fp32 and casts to the model dtype)
-//   kcache/vcache [max_ctx][H]
-__global__ void __launch_bounds__(256) rope_append_kernel(__half* __restrict__ qkv, const __half* __restrict__ cos_t,
-                                                           const __half* __restrict__ sin_t, const int* __restrict__ pos_p,
-                                                           __half* __restrict__ kcache, __half* __restrict__ vcache, int H, int D)
-{
-    pdl_launch_dependents();
-    pdl_wait_prior_grids();
-    const int pos  = *pos_p;
-    const int half = D / 2;
-    const int idx  = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (head, i < D/2)
-    if (idx >= H / 2)
-        return;
-    const int head = idx / half;
-    const int i    = idx - head * half;
-    const float c  = __half2float(cos_t[int64_t(pos) * half + i]);
-    const float s  = __half2float(sin_t[int64_t(pos) * half + i]);
-    const int a    = head * D + i;
-    const int b    = a + half;
-    {
-        const float q0 = __half2float(qkv[a]), q1 = __half2float(qkv[b]);
-        // HF: q*cos + rotate_half(q)*sin evaluated in fp16: each product and the sum are rounded
-        qkv[a] = __hadd(__float2half_rn(q0 * c), __float2half_rn(-q1 * s));
-        qkv[b] = __hadd(__float2half_rn(q1 * c), __float2half_rn(q0 * s));
-    }
-    {
-        const float k0 = __half2float(qkv[H + a]), k1 = __half2float(qkv[H + b]);
-        kcache[int64_t(pos) * H + a] = __hadd(__float2half_rn(k0 * c), __float2half_rn(-k1 * s));
-        kcache[int64_t(pos) * H + b] = __hadd(__float2half_rn(k1 * c), __float2half_rn(k0 * s));
-    }
-    vcache[int64_t(pos) * H + a] = qkv[2 * H + a];
-    vcache[int64_t(pos) * H + b] = qkv[2 * H + b];
-}
-
-// Split-KV decode attention, one query token.  grid = (heads, splits), 128 threads, head_dim 128.
-//   partial[(head*splits + split)] = { o[128] (unnormalised fp32), m, l }
+// ---------------------------------------------------------------------------------------------------------------
+// Fused RoPE + KV-append + split-KV decode attention + split merge, one query token, ONE launch per layer.
+//   grid = (heads, splits), 128 threads, head_dim 128.  Each CTA owns <= 64 cache positions: thread (rowlane = t/16,
+//   sub = t%16) holds 16-byte slices of 8 K rows and 8 V rows IN REGISTERS -- all 16 loads are issued up front (256 B in
+//   flight per thread), so the whole KV read of the layer is in flight at once and the kernel is a pure HBM stream.
+//   The CTA that owns the newest position rotates k, appends k/v to the cache and uses them from shared memory.
+//   Partials {o[128], m, l} go to scratch; the last CTA of a head (atomic ticket, self-resetting) merges them.
+// ---------------------------------------------------------------------------------------------------------------
 constexpr int ATT_D       = 128;
 constexpr int ATT_THREADS = 128;
-constexpr int ATT_MAXCHUNK = 512;  // positions per split held in smem
+constexpr int ATT_ROWS    = 64;  // cache positions per CTA (8 per rowlane)
 
-__global__ void __launch_bounds__(ATT_THREADS) attn_split_kernel(const __half* __restrict__ q, const __half* __restrict__ kcache,
-                                                                  const __half* __restrict__ vcache, const int* __restrict__ pos_p,
-                                                                  float* __restrict__ partial, int H, float scale)
+__device__ __forceinline__ float dot8(const uint4& kv, const float (&q)[8])
 {
-    __shared__ float sc[ATT_MAXCHUNK];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&kv.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&kv.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&kv.z));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&kv.w));
+    return q[0] * a.x + q[1] * a.y + q[2] * b.x + q[3] * b.y + q[4] * c.x + q[5] * c.y + q[6] * d.x + q[7] * d.y;
+}
+__device__ __forceinline__ void axpy8(float p, const uint4& vv, float (&acc)[8])
+{
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vv.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&vv.z));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&vv.w));
+    acc[0] = fmaf(p, a.x, acc[0]); acc[1] = fmaf(p, a.y, acc[1]); acc[2] = fmaf(p, b.x, acc[2]); acc[3] = fmaf(p, b.y, acc[3]);
+    acc[4] = fmaf(p, c.x, acc[4]); acc[5] = fmaf(p, c.y, acc[5]); acc[6] = fmaf(p, d.x, acc[6]); acc[7] = fmaf(p, d.y, acc[7]);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cos_t,
+                                                                  const __half* __restrict__ sin_t, const int* __restrict__ pos_p,
+                                                                  __half* __restrict__ kcache, __half* __restrict__ vcache,
+                                                                  float* __restrict__ partial, int* __restrict__ tickets,
+                                                                  __half* __restrict__ out, int H, float scale)
+{
+    __shared__ float q_s[ATT_D];
+    __shared__ __align__(16) __half knew[ATT_D];
+    __shared__ __align__(16) __half vnew[ATT_D];
+    __shared__ float sc[ATT_ROWS];
     __shared__ float red[ATT_THREADS / 32];
+    __shared__ float osum[8][ATT_D];
+    __shared__ int is_last_s;
+
+    const int t       = threadIdx.x;
+    const int lane    = t & 31;
+    const int warp    = t >> 5;
+    const int sub     = t & 15;   // which 8-dim slice of the head
+    const int rowlane = t >> 4;   // 0..7
+    const int head    = blockIdx.x;
+    const int splits  = gridDim.y;
+    const int split   = blockIdx.y;
+
     pdl_launch_dependents();
     pdl_wait_prior_grids();
-    const int L      = *pos_p + 1;  // attend to positions [0, pos]
-    const int head   = blockIdx.x;
-    const int splits = gridDim.y;
-    const int split  = blockIdx.y;
-    const int p0     = int((int64_t(split) * L) / splits);
-    const int p1     = int((int64_t(split + 1) * L) / splits);
-    const int n      = p1 - p0;
-    const int lane   = threadIdx.x & 31;
-    const int warp   = threadIdx.x >> 5;
-    float* out       = partial + (int64_t(head) * splits + split) * (ATT_D + 2);
 
-    // q slice of this lane: 4 consecutive dims
-    float qf[4];
-    {
-        const uint2 raw = *reinterpret_cast<const uint2*>(q + head * ATT_D + lane * 4);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-        qf[0] = a.x * scale; qf[1] = a.y * scale; qf[2] = b.x * scale; qf[3] = b.y * scale;
+    const int pos  = *pos_p;
+    const int L    = pos + 1;  // attend to positions [0, pos]
+    const int p0   = int((int64_t(split) * L) / splits);
+    const int p1   = int((int64_t(split + 1) * L) / splits);
+    const int n    = p1 - p0;                       // <= ATT_ROWS by construction of `splits`
+    const bool owns_new = (split == splits - 1);    // the last split always contains position pos
+    const int n_cache   = owns_new ? n - 1 : n;     // rows read from the cache
+
+    // issue every cache load first (K then V): 16 x 16 B per thread
+    uint4 kreg[8], vreg[8];
+    const __half* kbase = kcache + int64_t(p0) * H + head * ATT_D + sub * 8;
+    const __half* vbase = vcache + int64_t(p0) * H + head * ATT_D + sub * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = i * 8 + rowlane;
+        kreg[i]     = (j < n_cache) ? ldg_stream_128(kbase + int64_t(j) * H) : make_uint4(0u, 0u, 0u, 0u);
     }
-    // scores: each warp takes positions warp, warp+4, ... (4 in flight)
-    for (int j0 = warp * 4; j0 < n; j0 += 16) {
-        float d[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u;
-            d[u] = 0.f;
-            if (j < n) {
-                const uint2 raw = *reinterpret_cast<const uint2*>(kcache + int64_t(p0 + j) * H + head * ATT_D + lane * 4);
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-                d[u] = qf[0] * a.x + qf[1] * a.y + qf[2] * b.x + qf[3] * b.y;
-            }
+    for (int i = 0; i < 8; ++i) {
+        const int j = i * 8 + rowlane;
+        vreg[i]     = (j < n_cache) ? ldg_stream_128(vbase + int64_t(j) * H) : make_uint4(0u, 0u, 0u, 0u);
+    }
+
+    // RoPE of q (every CTA) and of the new k (owner CTA); HF rotate_half convention evaluated in fp16
+    if (t < ATT_D / 2) {
+        const float c = __half2float(cos_t[int64_t(pos) * (ATT_D / 2) + t]);
+        const float s = __half2float(sin_t[int64_t(pos) * (ATT_D / 2) + t]);
+        const int a = head * ATT_D + t, b = a + ATT_D / 2;
+        const float q0 = __half2float(qkv[a]), q1 = __half2float(qkv[b]);
+        q_s[t]             = __half2float(__hadd(__float2half_rn(q0 * c), __float2half_rn(-q1 * s))) * scale;
+        q_s[t + ATT_D / 2] = __half2float(__hadd(__float2half_rn(q1 * c), __float2half_rn(q0 * s))) * scale;
+        if (owns_new) {
+            const float k0 = __half2float(qkv[H + a]), k1 = __half2float(qkv[H + b]);
+            const __half r0 = __hadd(__float2half_rn(k0 * c), __float2half_rn(-k1 * s));
+            const __half r1 = __hadd(__float2half_rn(k1 * c), __float2half_rn(k0 * s));
+            knew[t] = r0; knew[t + ATT_D / 2] = r1;
+            kcache[int64_t(pos) * H + a] = r0; kcache[int64_t(pos) * H + b] = r1;
+            const __half v0 = qkv[2 * H + a], v1 = qkv[2 * H + b];
+            vnew[t] = v0; vnew[t + ATT_D / 2] = v1;
+            vcache[int64_t(pos) * H + a] = v0; vcache[int64_t(pos) * H + b] = v1;
         }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1)
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
-        const float mine = (lane == 0) ? d[0] : (lane == 1) ? d[1] : (lane == 2) ? d[2] : d[3];
-        if (lane < 4 && j0 + lane < n)
-            sc[j0 + lane] = mine;
     }
     __syncthreads();
-    // chunk max
-    float m = -INFINITY;
-    for (int j = threadIdx.x; j < n; j += ATT_THREADS)
-        m = fmaxf(m, sc[j]);
+
+    float qf[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+        qf[d] = q_s[sub * 8 + d];
+
+    // scores: 16 lanes share a row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = i * 8 + rowlane;
+        uint4 kv    = kreg[i];
+        if (owns_new && j == n - 1)
+            kv = *reinterpret_cast<const uint4*>(&knew[sub * 8]);
+        float d = dot8(kv, qf);
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1)
+            d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (sub == 0 && j < n)
+            sc[j] = d;
+    }
+    __syncthreads();
+
+    // softmax statistics of this chunk
+    float m = (t < n) ? sc[t] : -INFINITY;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1)
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -173,57 +199,71 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_split_kernel(const __half* _
     __syncthreads();
     m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
     __syncthreads();
-    float l = 0.f;
-    for (int j = threadIdx.x; j < n; j += ATT_THREADS) {
-        const float e = __expf(sc[j] - m);
-        sc[j] = e;
-        l += e;
+    float e = 0.f;
+    if (t < n) {
+        e     = __expf(sc[t] - m);
+        sc[t] = e;
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1)
-        l += __shfl_xor_sync(0xffffffffu, l, o);
+        e += __shfl_xor_sync(0xffffffffu, e, o);
     if (lane == 0)
-        red[warp] = l;
+        red[warp] = e;
     __syncthreads();
-    l = red[0] + red[1] + red[2] + red[3];
-    // o[d] = sum_j p_j * V[j][d]; thread = d
-    const int dcol = threadIdx.x;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const __half* vp = vcache + int64_t(p0) * H + head * ATT_D + dcol;
-    int j = 0;
-    for (; j + 4 <= n; j += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            acc[u] = fmaf(sc[j + u], __half2float(vp[int64_t(j + u) * H]), acc[u]);
-    }
-    for (; j < n; ++j)
-        acc[0] = fmaf(sc[j], __half2float(vp[int64_t(j) * H]), acc[0]);
-    out[dcol] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    if (threadIdx.x == 0) {
-        out[ATT_D]     = (n > 0) ? m : -INFINITY;
-        out[ATT_D + 1] = (n > 0) ? l : 0.f;
-    }
-}
+    const float l = red[0] + red[1] + red[2] + red[3];
 
-// merge the split partials: out[head*128 + d] = sum_s w_s o_s[d] / sum_s w_s l_s,  w_s = exp(m_s - m)
-__global__ void __launch_bounds__(ATT_THREADS) attn_combine_kernel(const float* __restrict__ partial, __half* __restrict__ out,
-                                                                    int splits)
-{
-    pdl_launch_dependents();
-    pdl_wait_prior_grids();
-    const int head = blockIdx.x;
-    const float* p = partial + int64_t(head) * splits * (ATT_D + 2);
-    float m = -INFINITY;
-    for (int s = 0; s < splits; ++s)
-        m = fmaxf(m, p[s * (ATT_D + 2) + ATT_D]);
-    float num = 0.f, den = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        const float ms = p[s * (ATT_D + 2) + ATT_D];
-        const float w  = (ms == -INFINITY) ? 0.f : __expf(ms - m);
-        num = fmaf(w, p[s * (ATT_D + 2) + threadIdx.x], num);
-        den = fmaf(w, p[s * (ATT_D + 2) + ATT_D + 1], den);
+    // o = sum_j p_j V_j : each thread accumulates its 8 dims over its rows, then the 8 rowlanes are summed in smem
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = i * 8 + rowlane;
+        if (j < n) {
+            uint4 vv = vreg[i];
+            if (owns_new && j == n - 1)
+                vv = *reinterpret_cast<const uint4*>(&vnew[sub * 8]);
+            axpy8(sc[j], vv, acc);
+        }
     }
-    out[head * ATT_D + threadIdx.x] = __float2half_rn(num / den);
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+        osum[rowlane][sub * 8 + d] = acc[d];
+    __syncthreads();
+    float o = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        o += osum[r][t];
+
+    float* mine = partial + (int64_t(head) * splits + split) * (ATT_D + 2);
+    mine[t] = o;
+    if (t == 0) {
+        mine[ATT_D]     = (n > 0) ? m : -INFINITY;
+        mine[ATT_D + 1] = (n > 0) ? l : 0.f;
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        const int old = atomicAdd(tickets + head, 1);
+        const int last = (old == splits - 1) ? 1 : 0;
+        if (last)
+            tickets[head] = 0;  // self-cleaning for the next launch
+        is_last_s = last;
+    }
+    __syncthreads();
+    if (is_last_s) {
+        __threadfence();
+        const float* p = partial + int64_t(head) * splits * (ATT_D + 2);
+        float mm = -INFINITY;
+        for (int s2 = 0; s2 < splits; ++s2)
+            mm = fmaxf(mm, __ldcg(p + s2 * (ATT_D + 2) + ATT_D));
+        float num = 0.f, den = 0.f;
+        for (int s2 = 0; s2 < splits; ++s2) {
+            const float ms = __ldcg(p + s2 * (ATT_D + 2) + ATT_D);
+            const float w  = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
+            num = fmaf(w, __ldcg(p + s2 * (ATT_D + 2) + t), num);
+            den = fmaf(w, __ldcg(p + s2 * (ATT_D + 2) + ATT_D + 1), den);
+        }
+        out[head * ATT_D + t] = __float2half_rn(num / den);
+    }
 }
 
 }  // namespace
@@ -257,40 +297,30 @@ int eetq_b200_decode_rmsnorm(const void* x, const void* w, void* y, int64_t M, i
     return EETQ_B200_OK;
 }
 
-int eetq_b200_decode_rope_append(void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache, void* vcache,
-                                 int64_t H, int64_t D, int pdl, void* stream)
-{
-    EB_CHECK_ARG(qkv && cos_t && sin_t && pos_i32 && kcache && vcache && H % D == 0 && D % 2 == 0, "decode_rope_append: bad argument");
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
-    launch_cfg(cfg, attr, dim3(unsigned((H / 2 + 255) / 256)), dim3(256), 0, pdl != 0, static_cast<cudaStream_t>(stream));
-    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rope_append_kernel, static_cast<__half*>(qkv), static_cast<const __half*>(cos_t),
-                                     static_cast<const __half*>(sin_t), static_cast<const int*>(pos_i32),
-                                     static_cast<__half*>(kcache), static_cast<__half*>(vcache), int(H), int(D)));
-    count_launch();
-    return EETQ_B200_OK;
-}
+// Number of KV splits the fused attention kernel needs for a cache of max_ctx positions (<= 64 positions per CTA).
+int64_t eetq_b200_decode_attention_splits(int64_t max_ctx) { return (max_ctx + ATT_ROWS - 1) / ATT_ROWS; }
 
-// attention for one token over cache positions [0, *pos]; partial: heads*splits*(128+2) floats of scratch.
-int eetq_b200_decode_attention(const void* q, const void* kcache, const void* vcache, const void* pos_i32, void* partial,
-                               void* out, int64_t H, int64_t D, int64_t splits, int64_t max_ctx, int pdl, void* stream)
+// Fused RoPE + KV append + attention for one token at position *pos (reads [0, pos], writes cache row pos).
+//   qkv [3H] raw projections (not modified); partial: (H/D) * splits * 130 floats scratch; tickets: H/D ints, ZERO on
+//   first use (the kernel leaves them zero); out [H].
+int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
+                               void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
+                               int pdl, void* stream)
 {
-    EB_CHECK_ARG(q && kcache && vcache && pos_i32 && partial && out, "decode_attention: null pointer argument");
+    EB_CHECK_ARG(qkv && cos_t && sin_t && pos_i32 && kcache && vcache && partial && tickets && out,
+                 "decode_attention: null pointer argument");
     EB_CHECK_ARG(D == ATT_D && H % D == 0, "decode_attention: head_dim must be 128");
-    EB_CHECK_ARG(splits >= 1 && (max_ctx + splits - 1) / splits + 1 <= ATT_MAXCHUNK,
-                 "decode_attention: max_ctx/splits must be < %d positions", ATT_MAXCHUNK);
-    const int heads = int(H / D);
-    cudaStream_t s  = static_cast<cudaStream_t>(stream);
+    EB_CHECK_ARG(max_ctx >= 1 && max_ctx <= (1 << 20), "decode_attention: bad max_ctx");
+    const int heads  = int(H / D);
+    const int splits = int(eetq_b200_decode_attention_splits(max_ctx));
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    launch_cfg(cfg, attr, dim3(unsigned(heads), unsigned(splits)), dim3(ATT_THREADS), 0, pdl != 0, s);
-    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_split_kernel, static_cast<const __half*>(q), static_cast<const __half*>(kcache),
-                                     static_cast<const __half*>(vcache), static_cast<const int*>(pos_i32),
-                                     static_cast<float*>(partial), int(H), 1.0f / sqrtf(float(D))));
-    launch_cfg(cfg, attr, dim3(unsigned(heads)), dim3(ATT_THREADS), 0, pdl != 0, s);
-    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_combine_kernel, static_cast<const float*>(partial), static_cast<__half*>(out),
-                                     int(splits)));
-    count_launch(2);
+    launch_cfg(cfg, attr, dim3(unsigned(heads), unsigned(splits)), dim3(ATT_THREADS), 0, pdl != 0, static_cast<cudaStream_t>(stream));
+    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_fused_kernel, static_cast<const __half*>(qkv), static_cast<const __half*>(cos_t),
+                                     static_cast<const __half*>(sin_t), static_cast<const int*>(pos_i32), static_cast<__half*>(kcache),
+                                     static_cast<__half*>(vcache), static_cast<float*>(partial), static_cast<int*>(tickets),
+                                     static_cast<__half*>(out), int(H), 1.0f / sqrtf(float(D))));
+    count_launch();
     return EETQ_B200_OK;
 }
 

@@ -27,6 +27,8 @@
 //     dependent launch the HBM stream of layer i+1 starts while layer i drains.
 //
 // Algorithmic bytes per call: K*N + 2*N + 2*M*K + 2*M*N; each weight byte is read exactly once.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eetq_b200 {
@@ -270,6 +272,17 @@ struct Log2<8> {
 // dynamic smem: partial[row][m][warp] fp32
 extern __shared__ float gemv_partial[];
 
+// 0 = TMA-streamed kernel (default), 1 = register double-buffered LDG kernel; EETQ_B200_GEMV_IMPL=ldg selects 1
+int gemv_impl()
+{
+    static int impl = -1;
+    if (impl < 0) {
+        const char* e = getenv("EETQ_B200_GEMV_IMPL");
+        impl          = (e != nullptr && e[0] == 'l') ? 1 : 0;
+    }
+    return impl;
+}
+
 constexpr __host__ __device__ int min_ctas(int M, int KITERS, bool XREG) { return (XREG && M * KITERS <= 4) ? 2 : 1; }
 
 // Optional fusions around the GEMV (decode-side glue folded into the hot kernel; all pointers may be null):
@@ -480,6 +493,278 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
     }
 }
 
+// =====================================================================================================================
+// TMA-streamed variant (default): the CTA's rows are ONE contiguous byte range of the b200 layout, so a single
+// producer thread streams it with cp.async.bulk (TMA 1-D) into a shared-memory ring (~96 KB/CTA, one CTA per SM) and
+// runs AHEAD of the consumers -- across stages and, under programmatic dependent launch, across kernels: the next
+// GEMV's CTA co-resides (low register / half the smem) and fills its ring while this kernel is still streaming,
+// so HBM never idles at kernel boundaries.  The 8 consumer warps read the ring with conflict-free LDS.128 (thread t
+// owns 16-byte K-chunk t of every row, activation slice in registers) and do the same PRMT + FHFMA arithmetic.
+// =====================================================================================================================
+constexpr int kConsumers      = 256;              // 8 consumer warps
+constexpr int kStreamThreads  = kConsumers + 32;  // + 1 producer warp
+constexpr int kMaxStages      = 16;
+constexpr int kRingBytes      = 96 * 1024;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GEMV_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GEMV_DONE;\n"
+        "bra GEMV_WAIT;\n"
+        "GEMV_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared, completion on an mbarrier, L2 evict-first (weights are read once per token)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+// dynamic smem layout: [ring: stages * stage_bytes][partial: padded_rows * M * 8 floats]
+template <typename T, int M, int KITERS, int R>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+    w8a16_gemv_stream_kernel(const T* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ w, const T* __restrict__ scales,
+                             const T* __restrict__ bias, T* __restrict__ y, int64_t ldy, int N, int K, int stages, int stage_bytes,
+                             const GemvFuse<T> fuse)
+{
+    extern __shared__ __align__(128) uint8_t stream_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages];
+    __shared__ float red_smem[M][kConsumers / 32];
+
+    const int tid     = threadIdx.x;
+    const int lane    = tid & 31;
+    const int warp    = tid >> 5;
+    const int nchunks = K >> 4;
+
+    const int row_begin = int((int64_t(blockIdx.x) * N) / gridDim.x);
+    const int row_end   = int((int64_t(blockIdx.x + 1) * N) / gridDim.x);
+    const int nrows     = row_end - row_begin;
+    const int ngroups   = (nrows + R - 1) / R;  // one ring stage per group of R rows
+
+    const uint32_t full0  = smem_addr(&bars[0]);
+    const uint32_t empty0 = smem_addr(&bars[kMaxStages]);
+    float* partial        = reinterpret_cast<float*>(stream_smem + size_t(stages) * stage_bytes);
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, kConsumers / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_launch_dependents();  // the next kernel may start (and prefetch its own weights) as soon as it fits
+
+    if (warp == kConsumers / 32) {
+        // ================================================================= producer: runs ahead, independent of x
+        if (lane == 0) {
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            const uint8_t* src   = w + int64_t(row_begin) * K;
+            const uint32_t ring0 = smem_addr(stream_smem);
+            for (int g = 0; g < ngroups; ++g) {
+                const int s       = g % stages;
+                const uint32_t ph = (g / stages) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const int rows       = min(R, nrows - g * R);
+                const uint32_t bytes = uint32_t(rows) * uint32_t(K);
+                mbar_expect_tx(full0 + 8 * s, bytes);
+                // rows are adjacent in memory: the whole group is one contiguous range; issue it in <= 16 KB pieces
+                uint32_t done = 0;
+                while (done < bytes) {
+                    const uint32_t piece = min(bytes - done, 16384u);
+                    bulk_g2s(ring0 + uint32_t(s) * uint32_t(stage_bytes) + done, src + int64_t(g) * R * K + done, piece,
+                             full0 + 8 * s, policy);
+                    done += piece;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================================================================== consumers
+    pdl_wait_prior_grids();  // activations / residual come from the previous kernel
+
+    XSlice<T> xs[M][KITERS];
+    float xoff[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int i = 0; i < KITERS; ++i) {
+            const int c = tid + i * kConsumers;
+            if (c >= nchunks)
+                xs[m][i].zero();
+            else if (fuse.xmode == GEMV_X_SILU_MUL)
+                xs[m][i].load_silu_mul(x + int64_t(m) * ldx + int64_t(c) * 16, x + int64_t(m) * ldx + K + int64_t(c) * 16);
+            else
+                xs[m][i].load(x + int64_t(m) * ldx + int64_t(c) * 16);
+        }
+    if (fuse.xmode == GEMV_X_RMSNORM) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < KITERS; ++i)
+                ss += xs[m][i].sumsq();
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1)
+                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0)
+                red_smem[m][warp] = ss;
+        }
+        consumer_sync();
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            float tot = 0.f;
+#pragma unroll
+            for (int wi = 0; wi < kConsumers / 32; ++wi)
+                tot += red_smem[m][wi];
+            const float r = rsqrtf(tot / float(K) + fuse.eps);
+#pragma unroll
+            for (int i = 0; i < KITERS; ++i) {
+                const int c = tid + i * kConsumers;
+                if (c < nchunks)
+                    xs[m][i].apply_norm(r, fuse.norm_weight + int64_t(c) * 16);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        float so = 0.f;
+#pragma unroll
+        for (int i = 0; i < KITERS; ++i)
+            so += xs[m][i].sum;
+        xoff[m] = -XSlice<T>::kOffset * so;
+    }
+
+    for (int g = 0; g < ngroups; ++g) {
+        const int s       = g % stages;
+        const uint32_t ph = (g / stages) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        const uint8_t* stage = stream_smem + size_t(s) * stage_bytes;
+        uint4 wv[R][KITERS];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < KITERS; ++i) {
+                const int c = tid + i * kConsumers;
+                // rows beyond the group (ragged last group) hold stale bytes: their results are never stored
+                wv[r][i] = (c < nchunks) ? *reinterpret_cast<const uint4*>(stage + size_t(r) * K + size_t(c) * 16)
+                                         : make_uint4(0u, 0u, 0u, 0u);
+            }
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(empty0 + 8 * s);  // data is in registers: hand the stage back to the producer
+        float acc[M][R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                float a = xoff[m];
+#pragma unroll
+                for (int i = 0; i < KITERS; ++i)
+                    xs[m][i].dot(wv[r][i], a);
+                acc[m][r] = a;
+            }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const float tot = warp_reduce_rows<R>(acc[m], lane);
+            const int rid   = lane >> (5 - Log2<R>::v);
+            if ((lane & ((32 >> Log2<R>::v) - 1)) == 0)
+                partial[((g * R + rid) * M + m) * (kConsumers / 32) + warp] = tot;
+        }
+    }
+
+    consumer_sync();
+    for (int idx = tid; idx < nrows * M; idx += kConsumers) {
+        const int r = idx / M;
+        const int m = idx - r * M;
+        float sum   = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < kConsumers / 32; ++wi)
+            sum += partial[(r * M + m) * (kConsumers / 32) + wi];
+        const int n = row_begin + r;
+        float out   = sum * to_float(scales[n]);
+        if (bias != nullptr)
+            out += to_float(bias[n]);
+        T o = from_float<T>(out);
+        if (fuse.residual != nullptr)
+            o = from_float<T>(to_float(o) + to_float(fuse.residual[int64_t(m) * fuse.ldr + n]));
+        y[int64_t(m) * ldy + n] = o;
+    }
+}
+
+template <typename T, int M, int KITERS, int R>
+int launch_stream(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N, int K,
+                  const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
+{
+    const DeviceInfo& di = device_info();
+    if (!di.ok) {
+        set_error("gemv: device query failed");
+        return EETQ_B200_ECUDA;
+    }
+    auto kernel           = w8a16_gemv_stream_kernel<T, M, KITERS, R>;
+    const int stage_bytes = R * K;
+    int stages            = kRingBytes / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    int grid = di.sm_count;
+    if (grid > N) grid = N;
+    const int max_rows = (N + grid - 1) / grid;
+    if (stages > (max_rows + R - 1) / R) stages = (max_rows + R - 1) / R;  // never more stages than row groups
+    if (stages < 1) stages = 1;
+    const int padded  = ((max_rows + R - 1) / R) * R;
+    const size_t smem = size_t(stages) * stage_bytes + size_t(padded) * M * (kConsumers / 32) * sizeof(float);
+    if (smem > size_t(di.max_smem_optin) - 2048) {
+        set_error("gemv(stream): %zu bytes of shared memory needed (N=%d K=%d)", smem, N, K);
+        return EETQ_B200_EINVAL;
+    }
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        EB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin - 2048));
+        attr_set[dev] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim          = dim3(unsigned(grid));
+    cfg.blockDim         = dim3(kStreamThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream           = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, x, ldx, w, scales, bias, y, ldy, N, K, stages, stage_bytes, fuse);
+    count_launch();
+    if (e != cudaSuccess) {
+        set_error("gemv(stream) launch failed: %s", cudaGetErrorString(e));
+        return EETQ_B200_ECUDA;
+    }
+    return EETQ_B200_OK;
+}
+
 template <typename T, int M, int KITERS, int R, bool XREG>
 int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N,
                    int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
@@ -530,6 +815,19 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     const int kiters  = (nchunks + kThreads - 1) / kThreads;
     // register-resident activations while the slice stays small (fp16: 8 regs, bf16: 16 regs per 16 values)
     constexpr int kMaxXregIters = (DTypeOf<T>::value == EETQ_B200_F16) ? 8 / M : 4 / M;
+    // default: TMA-streamed kernel (rows per ring stage: 4 / 2 / 1 / 1 for K <= 4096 / 8192 / 12288 / 16384)
+    if (gemv_impl() == 0) {
+#define EB_STREAM_CASE(KI, RR)                                                                                          \
+    if (kiters == KI) {                                                                                                 \
+        if constexpr (M * KI <= 4 && KI <= kMaxXregIters)                                                               \
+            return launch_stream<T, M, KI, RR>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);               \
+    }
+        EB_STREAM_CASE(1, 4)
+        EB_STREAM_CASE(2, 2)
+        EB_STREAM_CASE(3, 1)
+        EB_STREAM_CASE(4, 1)
+#undef EB_STREAM_CASE
+    }
 #define EB_GEMV_CASE(KI, RS, RB)                                                                                        \
     if (kiters == KI) {                                                                                                 \
         if constexpr (KI <= kMaxXregIters)                                                                             \

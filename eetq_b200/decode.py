@@ -9,8 +9,8 @@ This is the caller either side of the hot path (SURVEY.md section 8 "next"), kep
                             implementation used as the numerical reference in tests.
 * ``W8A16LlamaDecoder``  -- takes the quantised model, fuses q|k|v and gate|up row-wise (trivial in the b200 layout:
                             rows are output features), and runs single-token decode as ONE CUDA graph of native kernels:
-                            per layer 4 streaming GEMVs (RMSNorm / SiLU*up / residual fused into them), RoPE+KV-append
-                            and split-KV attention, chained with programmatic dependent launch so that the weight
+                            per layer 4 streaming GEMVs (RMSNorm / SiLU*up / residual fused into them) and ONE fused
+                            RoPE + KV-append + split-KV attention kernel, chained with programmatic dependent launch so that the weight
                             stream of kernel i+1 starts while kernel i drains.
                             With ``world_size > 1`` every linear is column-sharded (rank r owns rows
                             [r*N/P, (r+1)*N/P) of each fused weight -- a contiguous byte range) and the activations are
@@ -192,8 +192,6 @@ class _ShardedLinear:
 
 
 class W8A16LlamaDecoder:
-    SPLITS = 8  # KV splits of the decode attention
-
     def __init__(self, model: nn.Module, shape: LlamaShape, max_ctx: int = 1280, pdl: bool = True, rank: int = 0, world_size: int = 1,
                  group=None):
         self.shape, self.max_ctx, self.pdl = shape, max_ctx, bool(pdl)
@@ -230,10 +228,12 @@ class W8A16LlamaDecoder:
         self.gu = torch.zeros(2 * I, dtype=dt, device=dev)
         self.xn = torch.zeros(1, H, dtype=dt, device=dev)
         self.logits = torch.zeros(1, shape.vocab, dtype=dt, device=dev)
-        self.partial = torch.zeros(shape.heads * self.SPLITS * (shape.head_dim + 2), dtype=torch.float32, device=dev)
+        self._L = _cabi.lib()
+        splits = int(self._L.eetq_b200_decode_attention_splits(max_ctx))
+        self.partial = torch.zeros(shape.heads * splits * (shape.head_dim + 2), dtype=torch.float32, device=dev)
+        self.tickets = torch.zeros(shape.heads, dtype=torch.int32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
-        self._L = _cabi.lib()
 
     # ------------------------------------------------------------------------------------------------- construction
     @classmethod
@@ -267,11 +267,9 @@ class W8A16LlamaDecoder:
         _cabi.check(L.eetq_b200_decode_embed(_vp(self.embed), _vp(self.token), _vp(self.x), H, pdl, st()), "decode_embed")
         for li, w in enumerate(self.layers):
             self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1)
-            _cabi.check(L.eetq_b200_decode_rope_append(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
-                                                       _vp(self.vcache[li]), H, D, pdl, st()), "decode_rope_append")
-            _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.kcache[li]), _vp(self.vcache[li]), _vp(self.pos),
-                                                     _vp(self.partial), _vp(self.attn), H, D, self.SPLITS, self.max_ctx, pdl, st()),
-                        "decode_attention")
+            _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
+                                                     _vp(self.vcache[li]), _vp(self.partial), _vp(self.tickets), _vp(self.attn), H, D,
+                                                     self.max_ctx, pdl, st()), "decode_attention")
             # x2 = x + o_proj(attn); x = x2 + down(silu(gate) * up)   (ping-pong so no kernel reads what it writes)
             self._gemv(self.attn, H, w["o"], self.x2, residual_full=self.x)
             self._gemv(self.x2, H, w["gu"], self.gu, norm_w=w["ln2"], xmode=1)

@@ -150,13 +150,15 @@ int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200,
 int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, int pdl, void* stream);
 /* y = RMSNorm(x) * w over M rows of H */
 int eetq_b200_decode_rmsnorm(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, int pdl, void* stream);
-/* RoPE (rotate_half convention; behaviour of rotary_embedding_neox, csrc/embedding_kernels/pos_encoding_kernels.cu:12-53)
- * on q,k of qkv = [q | k | v] (3*H) at position *pos, q rotated in place, k,v appended to the caches [max_ctx][H] */
-int eetq_b200_decode_rope_append(void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
-                                 void* vcache, int64_t H, int64_t D, int pdl, void* stream);
-/* one-token attention over cache positions [0, *pos]; head_dim 128; partial = H/D * splits * 130 floats scratch */
-int eetq_b200_decode_attention(const void* q, const void* kcache, const void* vcache, const void* pos_i32, void* partial,
-                               void* out, int64_t H, int64_t D, int64_t splits, int64_t max_ctx, int pdl, void* stream);
+/* Fused RoPE (rotate_half convention; behaviour of rotary_embedding_neox, csrc/embedding_kernels/pos_encoding_kernels.cu:12-53)
+ * + KV-cache append + split-KV attention + split merge for ONE token at position *pos, head_dim 128, ONE launch.
+ *   qkv [3H] = q | k | v raw projections; cos/sin [max_pos][D/2]; kcache/vcache [max_ctx][H] (row *pos is written);
+ *   partial: (H/D) * eetq_b200_decode_attention_splits(max_ctx) * 130 floats of scratch; tickets: H/D int32, zero on first
+ *   use (left zero); out [H]. */
+int64_t eetq_b200_decode_attention_splits(int64_t max_ctx);
+int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
+                               void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
+                               int pdl, void* stream);
 
 /* number of kernels this library has launched on this process so far (bench.py's gpu_launches) */
 uint64_t eetq_b200_launch_count(void);

@@ -105,4 +105,4 @@ def test_step_host_roundtrip(cuda):
         a.copy_(b)
     dec2 = W8A16LlamaDecoder.from_model(model, max_ctx=64)
     assert dec2.generate(prompt, 6)[1:] == seq
-    assert dec.launches_per_step == 1 + SMALL.layers * 7 + 1   # embed + per layer (4 GEMV + rope + 2 attention) + final norm
+    assert dec.launches_per_step == 1 + SMALL.layers * 5 + 1   # embed + per layer (4 GEMV + fused attention) + final norm
