@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
     const int split   = blockIdx.y;
 
     pdl_launch_dependents();
-    pdl_wait_prior_grids();
-
+    // `pos` and cache rows < pos were written by earlier STEPS (complete long before this launch), so they may be read
+    // before the dependency wait: the KV stream of this layer overlaps the tail of the preceding qkv GEMV.
     const int pos  = *pos_p;
     const int L    = pos + 1;  // attend to positions [0, pos]
     const int p0   = int((int64_t(split) * L) / splits);
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
         const int j = i * 8 + rowlane;
         vreg[i]     = (j < n_cache) ? ldg_stream_128(vbase + int64_t(j) * H) : make_uint4(0u, 0u, 0u, 0u);
     }
+    pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
 
     // RoPE of q (every CTA) and of the new k (owner CTA); HF rotate_half convention evaluated in fp16
     if (t < ATT_D / 2) {
@@ -252,15 +253,44 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
     if (is_last_s) {
         __threadfence();
         const float* p = partial + int64_t(head) * splits * (ATT_D + 2);
-        float mm = -INFINITY;
-        for (int s2 = 0; s2 < splits; ++s2)
-            mm = fmaxf(mm, __ldcg(p + s2 * (ATT_D + 2) + ATT_D));
-        float num = 0.f, den = 0.f;
-        for (int s2 = 0; s2 < splits; ++s2) {
-            const float ms = __ldcg(p + s2 * (ATT_D + 2) + ATT_D);
-            const float w  = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
-            num = fmaf(w, __ldcg(p + s2 * (ATT_D + 2) + t), num);
-            den = fmaf(w, __ldcg(p + s2 * (ATT_D + 2) + ATT_D + 1), den);
+        // merge: split statistics first (parallel over splits, staged in smem), then each thread merges its own dim with
+        // independent loads kept in flight (a serial chain of L2 round trips here used to cost more than the KV stream)
+        float mm = -INFINITY, den = 0.f, num = 0.f;
+        for (int base = 0; base < splits; base += ATT_ROWS) {
+            const int cnt = min(ATT_ROWS, splits - base);
+            __syncthreads();
+            if (t < cnt) {
+                sc[t]         = __ldcg(p + (base + t) * (ATT_D + 2) + ATT_D);       // m_s
+                osum[0][t]    = __ldcg(p + (base + t) * (ATT_D + 2) + ATT_D + 1);   // l_s
+            }
+            __syncthreads();
+            float cm = mm;
+            for (int s2 = 0; s2 < cnt; ++s2)
+                cm = fmaxf(cm, sc[s2]);
+            const float rescale = (mm == -INFINITY) ? 0.f : __expf(mm - cm);
+            num *= rescale;
+            den *= rescale;
+            mm = cm;
+            int s2 = 0;
+            for (; s2 + 4 <= cnt; s2 += 4) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = __ldcg(p + (base + s2 + u) * (ATT_D + 2) + t);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float ms = sc[s2 + u];
+                    const float w  = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
+                    num = fmaf(w, v[u], num);
+                    den = fmaf(w, osum[0][s2 + u], den);
+                }
+            }
+            for (; s2 < cnt; ++s2) {
+                const float ms = sc[s2];
+                const float w  = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
+                num = fmaf(w, __ldcg(p + (base + s2) * (ATT_D + 2) + t), num);
+                den = fmaf(w, osum[0][s2], den);
+            }
         }
         out[head * ATT_D + t] = __float2half_rn(num / den);
     }

@@ -272,18 +272,43 @@ struct Log2<8> {
 // dynamic smem: partial[row][m][warp] fp32
 extern __shared__ float gemv_partial[];
 
-// 0 = TMA-streamed kernel (default), 1 = register double-buffered LDG kernel; EETQ_B200_GEMV_IMPL=ldg selects 1
+// Kernel selection (development knobs, read once):
+//   EETQ_B200_GEMV_IMPL = ldg (default: register double-buffered LDG kernel) | tma (cp.async.bulk ring kernel)
+//   EETQ_B200_GEMV_CTAS = CTAs per SM the grid is sized for (default 2 for ldg, 1 for tma)
+//   EETQ_B200_GEMV_LOWREG = 1: ldg kernel compiled for 4 CTAs/SM (<= 64 registers) so that, under PDL, the next
+//                              kernel's CTAs co-reside and prefetch while this one streams
 int gemv_impl()
 {
     static int impl = -1;
     if (impl < 0) {
         const char* e = getenv("EETQ_B200_GEMV_IMPL");
-        impl          = (e != nullptr && e[0] == 'l') ? 1 : 0;
+        impl          = (e != nullptr && e[0] == 't') ? 0 : 1;
     }
     return impl;
 }
+int gemv_ctas_per_sm(int dflt)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("EETQ_B200_GEMV_CTAS");
+        v             = (e != nullptr) ? atoi(e) : 0;
+    }
+    return v > 0 ? v : dflt;
+}
+bool gemv_lowreg()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("EETQ_B200_GEMV_LOWREG");
+        v             = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
-constexpr __host__ __device__ int min_ctas(int M, int KITERS, bool XREG) { return (XREG && M * KITERS <= 4) ? 2 : 1; }
+constexpr __host__ __device__ int min_ctas(int M, int KITERS, bool XREG, bool LOW = false)
+{
+    return LOW ? (KITERS <= 2 ? 4 : 3) : ((XREG && M * KITERS <= 4) ? 2 : 1);
+}
 
 // Optional fusions around the GEMV (decode-side glue folded into the hot kernel; all pointers may be null):
 //   xmode GEMV_X_RMSNORM : the activation is RMS-normalised on load (x is the residual stream, norm_weight [K])
@@ -298,8 +323,8 @@ struct GemvFuse {
     int xmode;
 };
 
-template <typename T, int M, int KITERS, int R, bool XREG>
-__global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
+template <typename T, int M, int KITERS, int R, bool XREG, bool LOW = false>
+__global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG, LOW))
     w8a16_gemv_kernel(const T* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ w, const T* __restrict__ scales,
                       const T* __restrict__ bias, T* __restrict__ y, int64_t ldy, int N, int K, const GemvFuse<T> fuse)
 {
@@ -725,10 +750,11 @@ int launch_stream(const T* x, int64_t ldx, const uint8_t* w, const T* scales, co
     }
     auto kernel           = w8a16_gemv_stream_kernel<T, M, KITERS, R>;
     const int stage_bytes = R * K;
-    int stages            = kRingBytes / stage_bytes;
+    const int ctas        = gemv_ctas_per_sm(1);
+    int stages            = (kRingBytes / ctas) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
-    int grid = di.sm_count;
+    int grid = di.sm_count * ctas;
     if (grid > N) grid = N;
     const int max_rows = (N + grid - 1) / grid;
     if (stages > (max_rows + R - 1) / R) stages = (max_rows + R - 1) / R;  // never more stages than row groups
@@ -765,7 +791,7 @@ int launch_stream(const T* x, int64_t ldx, const uint8_t* w, const T* scales, co
     return EETQ_B200_OK;
 }
 
-template <typename T, int M, int KITERS, int R, bool XREG>
+template <typename T, int M, int KITERS, int R, bool XREG, bool LOW = false>
 int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N,
                    int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
@@ -774,9 +800,9 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
         set_error("gemv: device query failed");
         return EETQ_B200_ECUDA;
     }
-    constexpr int kCtasPerSm = min_ctas(M, KITERS, XREG);
+    constexpr int kCtasPerSm = LOW ? 2 : min_ctas(M, KITERS, XREG);
     constexpr int kMaxRows   = 96;  // rows per CTA bound (sizes the partial-sum buffer)
-    int grid                 = di.sm_count * kCtasPerSm;
+    int grid                 = di.sm_count * gemv_ctas_per_sm(kCtasPerSm);
     // keep rows/CTA <= kMaxRows, and grid a multiple of the SM count
     while ((N + grid - 1) / grid > kMaxRows)
         grid += di.sm_count;
@@ -798,7 +824,7 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
     cfg.numAttrs                                       = pdl ? 1 : 0;
 
     const cudaError_t e =
-        cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG>, x, ldx, w, scales, bias, y, ldy, N, K, fuse);
+        cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG, LOW>, x, ldx, w, scales, bias, y, ldy, N, K, fuse);
     count_launch();
     if (e != cudaSuccess) {
         set_error("gemv launch failed: %s", cudaGetErrorString(e));
@@ -827,6 +853,13 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
         EB_STREAM_CASE(3, 1)
         EB_STREAM_CASE(4, 1)
 #undef EB_STREAM_CASE
+    }
+    if (gemv_lowreg()) {
+        if constexpr (M == 1 && DTypeOf<T>::value == EETQ_B200_F16) {
+            if (kiters == 1) return launch_variant<T, 1, 1, 4, true, true>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            if (kiters == 2) return launch_variant<T, 1, 2, 2, true, true>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            if (kiters == 3) return launch_variant<T, 1, 3, 1, true, true>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        }
     }
 #define EB_GEMV_CASE(KI, RS, RB)                                                                                        \
     if (kiters == KI) {                                                                                                 \
