@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
                                                                   const __half* __restrict__ sin_t, const int* __restrict__ pos_p,
                                                                   __half* __restrict__ kcache, __half* __restrict__ vcache,
                                                                   float* __restrict__ partial, int* __restrict__ tickets,
-                                                                  __half* __restrict__ out, int H, float scale)
+                                                                  __half* __restrict__ out, int H, int max_ctx, float scale)
 {
     __shared__ float q_s[ATT_D];
     __shared__ __align__(16) __half knew[ATT_D];
@@ -134,17 +134,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
 
     // issue every cache load first (K then V): 16 x 16 B per thread
     uint4 kreg[8], vreg[8];
-    const __half* kbase = kcache + int64_t(p0) * H + head * ATT_D + sub * 8;
-    const __half* vbase = vcache + int64_t(p0) * H + head * ATT_D + sub * 8;
+    // cache layout [head][max_ctx][128]: the <= 64 rows of this CTA are ONE contiguous 16 KB block per tensor
+    const __half* kbase = kcache + (int64_t(head) * max_ctx + p0) * ATT_D + sub * 8;
+    const __half* vbase = vcache + (int64_t(head) * max_ctx + p0) * ATT_D + sub * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int j = i * 8 + rowlane;
-        kreg[i]     = (j < n_cache) ? ldg_stream_128(kbase + int64_t(j) * H) : make_uint4(0u, 0u, 0u, 0u);
+        kreg[i]     = (j < n_cache) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int j = i * 8 + rowlane;
-        vreg[i]     = (j < n_cache) ? ldg_stream_128(vbase + int64_t(j) * H) : make_uint4(0u, 0u, 0u, 0u);
+        vreg[i]     = (j < n_cache) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
     }
     pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
 
@@ -161,10 +162,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
             const __half r0 = __hadd(__float2half_rn(k0 * c), __float2half_rn(-k1 * s));
             const __half r1 = __hadd(__float2half_rn(k1 * c), __float2half_rn(k0 * s));
             knew[t] = r0; knew[t + ATT_D / 2] = r1;
-            kcache[int64_t(pos) * H + a] = r0; kcache[int64_t(pos) * H + b] = r1;
+            const int64_t row = (int64_t(head) * max_ctx + pos) * ATT_D;
+            kcache[row + t] = r0; kcache[row + t + ATT_D / 2] = r1;
             const __half v0 = qkv[2 * H + a], v1 = qkv[2 * H + b];
             vnew[t] = v0; vnew[t + ATT_D / 2] = v1;
-            vcache[int64_t(pos) * H + a] = v0; vcache[int64_t(pos) * H + b] = v1;
+            vcache[row + t] = v0; vcache[row + t + ATT_D / 2] = v1;
         }
     }
     __syncthreads();
@@ -331,7 +333,7 @@ int eetq_b200_decode_rmsnorm(const void* x, const void* w, void* y, int64_t M, i
 int64_t eetq_b200_decode_attention_splits(int64_t max_ctx) { return (max_ctx + ATT_ROWS - 1) / ATT_ROWS; }
 
 // Fused RoPE + KV append + attention for one token at position *pos (reads [0, pos], writes cache row pos).
-//   qkv [3H] raw projections (not modified); partial: (H/D) * splits * 130 floats scratch; tickets: H/D ints, ZERO on
+//   qkv [3H] raw projections (not modified); kcache/vcache [H/D][max_ctx][D] (head-major); partial: (H/D) * splits * 130 floats scratch; tickets: H/D ints, ZERO on
 //   first use (the kernel leaves them zero); out [H].
 int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
                                void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
@@ -349,7 +351,7 @@ int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* s
     EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_fused_kernel, static_cast<const __half*>(qkv), static_cast<const __half*>(cos_t),
                                      static_cast<const __half*>(sin_t), static_cast<const int*>(pos_i32), static_cast<__half*>(kcache),
                                      static_cast<__half*>(vcache), static_cast<float*>(partial), static_cast<int*>(tickets),
-                                     static_cast<__half*>(out), int(H), 1.0f / sqrtf(float(D))));
+                                     static_cast<__half*>(out), int(H), int(max_ctx), 1.0f / sqrtf(float(D))));
     count_launch();
     return EETQ_B200_OK;
 }

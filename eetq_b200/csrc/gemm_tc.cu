@@ -15,9 +15,9 @@
 //      D = fp32 accumulator in TMEM: lane = feature, column = token   (UMMA M = 128, N = BT, K = 16)
 //
 // Warp roles (320 threads):  warp 0 = TMA producer | warp 1 = tcgen05.mma issuer + TMEM alloc/dealloc |
-//                            warps 2..9 = dequantisers, then epilogue (TMEM -> regs -> global)
+//                            warps 2..9 = dequantisers (two groups of 4 on alternating k-blocks), then epilogue
 // Pipelines (mbarrier):      full/empty[STAGES] : TMA  <-> {dequant (int8 tile), MMA (activation tile)}
-//                            a_full/a_empty[2]  : dequant <-> MMA (fp16 A tile)
+//                            a_full/a_empty[4]  : dequant <-> MMA (fp16 A tile)
 //                            tmem_full          : MMA -> epilogue
 //
 // Arithmetic.  fp16: A = fp16(fp16(q) * s) with ONE rounding per weight and fp32 accumulation -- exactly the
@@ -44,14 +44,15 @@ namespace {
 constexpr int BLOCK_N      = 128;  // output features per CTA  (UMMA M)
 constexpr int BLOCK_K      = 64;   // k per pipeline stage (64 fp16 = one 128-byte swizzle row)
 constexpr int UMMA_K       = 16;
-constexpr int NUM_A_STAGES = 2;
+constexpr int NUM_A_STAGES = 4;   // fp16 A tiles in flight between the dequant groups and the MMA issuer
+constexpr int DQ_GROUPS    = 2;   // dequant warps work as 2 groups of 4 warps on alternating k-blocks
 constexpr int DQ_WARPS     = 8;
 constexpr int DQ_THREADS   = DQ_WARPS * 32;
 constexpr int TC_THREADS   = 64 + DQ_THREADS;  // warp 0 TMA, warp 1 MMA, 8 dequant/epilogue warps
 constexpr int W8_TILE      = BLOCK_N * BLOCK_K;       // 8192 B of int8
 constexpr int A_TILE       = BLOCK_N * BLOCK_K * 2;   // 16384 B of fp16/bf16
 
-__host__ __device__ constexpr int stages_for(int bt) { return bt >= 256 ? 4 : 6; }
+__host__ __device__ constexpr int stages_for(int bt) { return bt >= 256 ? 3 : (bt >= 128 ? 5 : 8); }
 __host__ __device__ constexpr int x_tile_bytes(int bt) { return bt * BLOCK_K * 2; }
 __host__ __device__ constexpr int smem_bytes_for(int bt)
 {
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_init(empty_bar + 8 * s, 1);
         }
         for (int a = 0; a < NUM_A_STAGES; ++a) {
-            mbar_init(afull_bar + 8 * a, DQ_THREADS);
+            mbar_init(afull_bar + 8 * a, DQ_WARPS / DQ_GROUPS);  // one elected arrive per warp of the owning group
             mbar_init(aempty_bar + 8 * a, 1);
         }
         mbar_init(tfull_bar, 1);
@@ -320,43 +321,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     else {
         // ============================================================== dequantisers, then epilogue
         const int dt = threadIdx.x - 64;  // 0..255
-        constexpr int CHUNKS_PER_THREAD = (W8_TILE / 16) / DQ_THREADS;  // 2
+        // Two groups of 4 warps convert alternating k-blocks, so one group's smem round trips and barrier hops overlap
+        // the other's; inside a group every thread batches its 4 LDS.128 before converting (ILP) and each warp
+        // signals the MMA issuer with ONE elected mbarrier arrive.
+        constexpr int GROUP_THREADS     = DQ_THREADS / DQ_GROUPS;             // 128
+        constexpr int CHUNKS_PER_THREAD = (W8_TILE / 16) / GROUP_THREADS;     // 4
+        const int grp = dt / GROUP_THREADS;
+        const int gt  = dt % GROUP_THREADS;
         // this thread always converts the same rows: fetch their channel scales once
         uint32_t scale2[CHUNKS_PER_THREAD];
 #pragma unroll
         for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
             scale2[j] = 0;
             if constexpr (SCALE_IN_A) {
-                const int n      = n_tile * BLOCK_N + ((dt + DQ_THREADS * j) >> 2);
+                const int n      = n_tile * BLOCK_N + ((gt + GROUP_THREADS * j) >> 2);
                 const __half sv  = (n < p.N) ? static_cast<const __half*>(p.scales)[n] : __ushort_as_half(0);
                 const __half2 s2 = __half2half2(sv);
                 scale2[j]        = *reinterpret_cast<const uint32_t*>(&s2);
             }
         }
-        for (int it = 0; it < num_kb; ++it) {
+        for (int it = grp; it < num_kb; it += DQ_GROUPS) {
             const int s       = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             const int a       = it % NUM_A_STAGES;
             const uint32_t aph = (it / NUM_A_STAGES) & 1;
             mbar_wait(full_bar + 8 * s, ph);          // int8 tile landed
-            mbar_wait(aempty_bar + 8 * a, aph ^ 1);   // A stage free
             const uint8_t* w8 = smem_gen + (w8_base - smem_base) + s * W8_TILE;
             uint8_t* at       = smem_gen + (a_base - smem_base) + a * A_TILE;
+            uint4 in[CHUNKS_PER_THREAD];
+#pragma unroll
+            for (int j = 0; j < CHUNKS_PER_THREAD; ++j)
+                in[j] = *reinterpret_cast<const uint4*>(w8 + (gt + GROUP_THREADS * j) * 16);
+            mbar_wait(aempty_bar + 8 * a, aph ^ 1);   // A stage free (the MMA that read it has completed)
 #pragma unroll
             for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
-                const int c   = dt + DQ_THREADS * j;  // 16-byte chunk index in the [128][64 B] int8 tile
+                const int c   = gt + GROUP_THREADS * j;  // 16-byte chunk index in the [128][64 B] int8 tile
                 const int row = c >> 2;
                 const int kc  = c & 3;
-                const uint4 in = *reinterpret_cast<const uint4*>(w8 + c * 16);
                 uint4 o0, o1;
-                dequant16<T>(in, scale2[j], o0, o1);
+                dequant16<T>(in[j], scale2[j], o0, o1);
                 // 128B swizzle: 16-byte chunk index XOR (row & 7)
                 uint8_t* rowp = at + row * 128;
                 *reinterpret_cast<uint4*>(rowp + (((2 * kc) ^ (row & 7)) << 4))     = o0;
                 *reinterpret_cast<uint4*>(rowp + (((2 * kc + 1) ^ (row & 7)) << 4)) = o1;
             }
             fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(afull_bar + 8 * a);
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(afull_bar + 8 * a);
         }
 
         // ---------------------------------------------------------- epilogue
@@ -529,16 +541,16 @@ struct TcConfig {
 
 TcConfig choose_config(int64_t M, int64_t N, int64_t K)
 {
+    // One CTA per SM (smem), 148 slots.  Dequantisation work scales with the number of token tiles, so up to 256
+    // tokens ride in ONE tile and spare SMs are filled by splitting K; above that, 256-token tiles.
     TcConfig c{};
     c.bt      = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     c.n_tiles = int((N + BLOCK_N - 1) / BLOCK_N);
     c.t_tiles = int((M + c.bt - 1) / c.bt);
-    const int tiles   = c.n_tiles * c.t_tiles;
-    const int kb      = int(K / BLOCK_K);
-    const int per_sm  = smem_bytes_for(c.bt) <= 113 * 1024 ? 2 : 1;
-    const int slots   = 148 * per_sm;
-    int s             = slots / tiles;
-    const int max_s   = kb / 8 > 0 ? kb / 8 : 1;  // at least 8 k-blocks (512 k) per split
+    const int tiles = c.n_tiles * c.t_tiles;
+    const int kb    = int(K / BLOCK_K);
+    int s           = 148 / tiles;
+    const int max_s = kb / 8 > 0 ? kb / 8 : 1;  // at least 8 k-blocks (512 k) per split
     if (s > max_s) s = max_s;
     if (s > 8) s = 8;
     if (s < 1) s = 1;

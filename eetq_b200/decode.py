@@ -216,8 +216,9 @@ class W8A16LlamaDecoder:
                 ln1=layer.input_layernorm.weight.detach(), ln2=layer.post_attention_layernorm.weight.detach()))
         H, I, L = shape.hidden, shape.inter, shape.layers
         self.cos, self.sin = rope_tables(shape, max_ctx, dev, dt)
-        self.kcache = torch.zeros(L, max_ctx, H, dtype=dt, device=dev)
-        self.vcache = torch.zeros(L, max_ctx, H, dtype=dt, device=dev)
+        # KV cache, head-major: [layer][head][max_ctx][head_dim] (each attention CTA streams one contiguous block)
+        self.kcache = torch.zeros(L, shape.heads, max_ctx, shape.head_dim, dtype=dt, device=dev)
+        self.vcache = torch.zeros(L, shape.heads, max_ctx, shape.head_dim, dtype=dt, device=dev)
         # decode-step buffers (device resident; the graph reads/writes these)
         self.token = torch.zeros(1, dtype=torch.int64, device=dev)
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -344,8 +345,8 @@ class W8A16LlamaDecoder:
             q = apply_rope(qkv[:, :H].reshape(T, s.heads, s.head_dim), cos, sin)
             k = apply_rope(qkv[:, H:2 * H].reshape(T, s.heads, s.head_dim), cos, sin)
             v = qkv[:, 2 * H:].reshape(T, s.heads, s.head_dim)
-            self.kcache[li, :T] = k.reshape(T, H)
-            self.vcache[li, :T] = v.reshape(T, H)
+            self.kcache[li, :, :T] = k.transpose(0, 1)
+            self.vcache[li, :, :T] = v.transpose(0, 1)
             o = F.scaled_dot_product_attention(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), is_causal=True)
             x = x + lin(o.transpose(0, 1).reshape(T, H), w["o"])
             gu = lin(rms(x, w["ln2"]), w["gu"])

@@ -152,7 +152,8 @@ int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, in
 int eetq_b200_decode_rmsnorm(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, int pdl, void* stream);
 /* Fused RoPE (rotate_half convention; behaviour of rotary_embedding_neox, csrc/embedding_kernels/pos_encoding_kernels.cu:12-53)
  * + KV-cache append + split-KV attention + split merge for ONE token at position *pos, head_dim 128, ONE launch.
- *   qkv [3H] = q | k | v raw projections; cos/sin [max_pos][D/2]; kcache/vcache [max_ctx][H] (row *pos is written);
+ *   qkv [3H] = q | k | v raw projections; cos/sin [max_pos][D/2]; kcache/vcache [H/D][max_ctx][D], head-major so each
+ *   CTA streams one contiguous block (row *pos of every head is written);
  *   partial: (H/D) * eetq_b200_decode_attention_splits(max_ctx) * 130 floats of scratch; tickets: H/D int32, zero on first
  *   use (left zero); out [H]. */
 int64_t eetq_b200_decode_attention_splits(int64_t max_ctx);

@@ -53,12 +53,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/kbench.json")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--tc-only", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     lib = _cabi.lib()
     results = []
-    shapes = [(4096, 4096), (4096, 12288), (4096, 22016), (11008, 4096)]
+    shapes = [(4096, 4096), (4096, 11008), (11008, 4096)] if args.tc_only else [(4096, 4096), (4096, 12288), (4096, 22016), (11008, 4096)]
 
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_gemv.so")
     ref = ctypes.CDLL(ref_path) if os.path.exists(ref_path) else None
@@ -68,7 +69,7 @@ def main():
         pool = max(2, (2 * L2_BYTES) // (K * N) + 1)
         ws = [torch.randint(-128, 128, (K, N), dtype=torch.int8, device=dev) for _ in range(pool)]
         sc = (torch.rand(N, device=dev) * 0.01).half()
-        for M in ([1, 2, 4] if not args.quick else [1]):
+        for M in ([] if args.tc_only else [1, 2, 4] if not args.quick else [1]):
             x = torch.randn(M, K, device=dev).half()
             for mode, pdl in ((1, False), (1, True)):
                 flags = _cabi.FLAG_FORCE_GEMV | (_cabi.FLAG_PDL if pdl else 0)
@@ -89,14 +90,15 @@ def main():
                 print(json.dumps(r), flush=True)
                 results.append(r)
         # torch fp16 GEMV/GEMM on dequantised weights for context (2 bytes/weight)
-        wf = [torch.randn(K, N, device=dev).half() for _ in range(max(2, pool // 2))]
-        x = torch.randn(1, K, device=dev).half()
-        fns = [(lambda w=w: torch.matmul(x, w)) for w in wf]
-        med, best = time_graph(fns)
-        r = dict(kernel="torch_fp16_matmul", K=K, N=N, M=1, us=med, gbs_fp16=(2 * K * N) / med / 1e3)
-        print(json.dumps(r), flush=True)
-        results.append(r)
-        del wf
+        if not args.tc_only:
+            wf = [torch.randn(K, N, device=dev).half() for _ in range(max(2, pool // 2))]
+            x = torch.randn(1, K, device=dev).half()
+            fns = [(lambda w=w: torch.matmul(x, w)) for w in wf]
+            med, best = time_graph(fns)
+            r = dict(kernel="torch_fp16_matmul", K=K, N=N, M=1, us=med, gbs_fp16=(2 * K * N) / med / 1e3)
+            print(json.dumps(r), flush=True)
+            results.append(r)
+            del wf
         for M in ([8, 16, 64, 256, 1024] if not args.quick else [16, 1024]):
             x = torch.randn(M, K, device=dev).half()
             fns = [(lambda w=w: w8_a16_gemm_bias(x, w, sc, None, flags=_cabi.FLAG_FORCE_TC)) for w in ws]
