@@ -334,7 +334,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{s.name} eet_quantize w8a16, batch 1, prompt {args.prompt} (real prefill), greedy decode",
                        "model": s.name, "global_batch": 1, "seq_len": args.prompt, "ctx_at_end": args.prompt + args.warmup + args.steps,
-                       "parallelism": "single-gpu" if world == 1 else f"column-sharded linears x{world} + NCCL all-gather of activations",
+                       "parallelism": "single-gpu" if world == 1 else f"column-sharded linears x{world} + all-gather of activations "
+                                      + ("fused into the GEMV epilogue over NVLink peer stores" if dec.allgather == "p2p" else "by ncclAllGather"),
                        "l2": "each step streams %.2f GB of int8 weights per GPU (>> 126 MB L2): inputs larger than L2, no flush" % (wbytes / 1e9),
                        "pdl": not args.no_pdl, "cuda_graph": True},
             "clocks": clocks,
@@ -349,8 +350,11 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # tearing down NCCL while CUDA graphs that captured collectives are alive can hang: flush and leave
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

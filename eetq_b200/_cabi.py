@@ -42,6 +42,8 @@ SIGNATURES = {
                                            _c_vp, _c_sz, _c_vp]),
     "eetq_b200_w8a16_gemv_fused": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp, _c_i64, _c_vp,
                                             _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
+    "eetq_b200_w8a16_gemv_fused_p2p": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp, _c_i64, _c_i64, _c_i64,
+                                                _c_i64, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "eetq_b200_decode_embed": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "eetq_b200_decode_rmsnorm": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_int, _c_vp]),
     "eetq_b200_decode_attention_splits": (_c_i64, [_c_i64]),

@@ -53,12 +53,25 @@ int launch_from_ref_layout(const uint8_t* w_ref, int64_t K, int64_t N, int8_t* q
 int launch_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t* w_ref, cudaStream_t stream);
 
 enum { GEMV_X_PLAIN = 0, GEMV_X_RMSNORM = 1, GEMV_X_SILU_MUL = 2 };
+// Fused all-gather over NVLink peer memory (column-sharded linears): instead of writing its output
+// slice locally and calling NCCL, the GEMV epilogue stores the slice into EVERY rank's activation buffer (peer-mapped
+// symmetric memory), then the last CTA publishes a per-call epoch flag on every peer and waits until all peers' flags
+// for the same call have arrived -- when the kernel completes, the full activation vector is present on this rank.
+struct GemvP2P {
+    unsigned long long peer_y[8]    = {};  // rank p's output buffer, already offset to THIS rank's first row
+    unsigned long long peer_flag[8] = {};  // address, on rank p, of flags[slot][this rank]
+    const unsigned* local_flags     = nullptr;  // this rank's flags[slot][0..world)
+    unsigned* ticket                = nullptr;  // local CTA ticket (zero between calls)
+    const int* epoch                = nullptr;  // device counter, strictly increasing per decode step
+    int world                       = 1;
+};
 struct GemvExtras {
     const void* norm_weight = nullptr;  // [K], GEMV_X_RMSNORM
     const void* residual    = nullptr;  // [M, N] row stride ldr
     int64_t ldr             = 0;
     float eps               = 0.f;
     int xmode               = GEMV_X_PLAIN;
+    GemvP2P p2p;
 };
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
                 int M, int64_t N, int64_t K, int dtype, const GemvExtras& ex, bool pdl, cudaStream_t stream);

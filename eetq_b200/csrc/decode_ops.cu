@@ -376,4 +376,37 @@ int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200,
     return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl != 0, static_cast<cudaStream_t>(stream));
 }
 
+
+// Column-sharded variant with the all-gather fused into the epilogue over NVLink peer memory (see GemvP2P in common.cuh).
+//   peer_y[r]    : rank r's copy of the FULL output vector, offset to this rank's first row (device-mapped peer pointer)
+//   peer_flag[r] : address on rank r of flags[slot][this rank];  local_flags: this rank's flags[slot][0..world)
+//   ticket       : local uint32, zero between calls;  epoch: device int32 that strictly increases every decode step
+int eetq_b200_w8a16_gemv_fused_p2p(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
+                                   float eps, int xmode, const void* residual, int64_t ldr, int64_t M, int64_t N_local, int64_t K,
+                                   int dtype, int world, const uint64_t* peer_y, const uint64_t* peer_flag, const void* local_flags,
+                                   void* ticket, const void* epoch, int64_t ldy, int pdl, void* stream)
+{
+    EB_CHECK_ARG(x && w_b200 && scales && peer_y && peer_flag && local_flags && ticket && epoch, "gemv_fused_p2p: null pointer argument");
+    EB_CHECK_ARG(world >= 2 && world <= 8, "gemv_fused_p2p: world must be in [2, 8]");
+    EB_CHECK_ARG(M >= 1 && M <= EETQ_B200_GEMV_MAX_M, "gemv_fused_p2p: M must be in [1, %d]", EETQ_B200_GEMV_MAX_M);
+    EB_CHECK_ARG(K > 0 && N_local > 0 && K % 64 == 0 && N_local % 64 == 0, "gemv_fused_p2p: K and N_local must be positive multiples of 64");
+    GemvExtras ex;
+    ex.norm_weight = norm_weight;
+    ex.residual    = residual;
+    ex.ldr         = ldr;
+    ex.eps         = eps;
+    ex.xmode       = xmode;
+    ex.p2p.world   = world;
+    for (int r = 0; r < world; ++r) {
+        ex.p2p.peer_y[r]    = peer_y[r];
+        ex.p2p.peer_flag[r] = peer_flag[r];
+    }
+    ex.p2p.local_flags = static_cast<const unsigned*>(local_flags);
+    ex.p2p.ticket      = static_cast<unsigned*>(ticket);
+    ex.p2p.epoch       = static_cast<const int*>(epoch);
+    void* y_self       = reinterpret_cast<void*>(peer_y[0]);  // unused in p2p mode (stores go through peer_y)
+    return launch_gemv(x, ldx, w_b200, scales, nullptr, y_self, ldy, int(M), N_local, K, dtype, ex, pdl != 0,
+                       static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -321,7 +321,55 @@ struct GemvFuse {
     int64_t ldr;
     float eps;
     int xmode;
+    GemvP2P p2p;
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long addr, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// store one output element locally or, for a column-sharded linear, into every rank's buffer
+template <typename T>
+__device__ __forceinline__ void store_out(T* y, int64_t idx, T o, const GemvP2P& pp)
+{
+    if (pp.world > 1) {
+#pragma unroll 1
+        for (int r = 0; r < pp.world; ++r)
+            reinterpret_cast<T*>(pp.peer_y[r])[idx] = o;
+    }
+    else {
+        y[idx] = o;
+    }
+}
+
+// after all stores of this CTA: publish + wait (last CTA only).  Must be called by every thread of the CTA.
+__device__ __forceinline__ void p2p_signal_and_wait(const GemvP2P& pp, int tid)
+{
+    if (pp.world <= 1)
+        return;
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned old = atomicAdd(pp.ticket, 1u);
+        if (old == gridDim.x - 1) {
+            *pp.ticket = 0;  // self-cleaning
+            __threadfence_system();
+            const unsigned epoch = unsigned(*pp.epoch);
+            for (int r = 0; r < pp.world; ++r)
+                st_release_sys(pp.peer_flag[r], epoch);
+            for (int r = 0; r < pp.world; ++r)
+                while (ld_acquire_sys(pp.local_flags + r) < epoch) {
+                }
+        }
+    }
+}
 
 template <typename T, int M, int KITERS, int R, bool XREG, bool LOW = false>
 __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG, LOW))
@@ -514,8 +562,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG, LOW))
         T o = from_float<T>(out);
         if (fuse.residual != nullptr)
             o = from_float<T>(to_float(o) + to_float(fuse.residual[int64_t(m) * fuse.ldr + n]));
-        y[int64_t(m) * ldy + n] = o;
+        store_out<T>(y, int64_t(m) * ldy + n, o, fuse.p2p);
     }
+    p2p_signal_and_wait(fuse.p2p, tid);
 }
 
 // =====================================================================================================================
@@ -842,7 +891,7 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     // register-resident activations while the slice stays small (fp16: 8 regs, bf16: 16 regs per 16 values)
     constexpr int kMaxXregIters = (DTypeOf<T>::value == EETQ_B200_F16) ? 8 / M : 4 / M;
     // default: TMA-streamed kernel (rows per ring stage: 4 / 2 / 1 / 1 for K <= 4096 / 8192 / 12288 / 16384)
-    if (gemv_impl() == 0) {
+    if (gemv_impl() == 0 && fuse.p2p.world <= 1) {
 #define EB_STREAM_CASE(KI, RR)                                                                                          \
     if (kiters == KI) {                                                                                                 \
         if constexpr (M * KI <= 4 && KI <= kMaxXregIters)                                                               \
@@ -906,13 +955,13 @@ int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales,
     const uint8_t* wu = reinterpret_cast<const uint8_t*>(w);
     if (dtype == EETQ_B200_F16) {
         using T = __half;
-        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode};
+        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p};
         return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
                              static_cast<T*>(y), ldy, M, int(N), int(K), f, pdl, stream);
     }
     if (dtype == EETQ_B200_BF16) {
         using T = __nv_bfloat16;
-        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode};
+        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p};
         return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
                              static_cast<T*>(y), ldy, M, int(N), int(K), f, pdl, stream);
     }

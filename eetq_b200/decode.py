@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -193,9 +194,11 @@ class _ShardedLinear:
 
 class W8A16LlamaDecoder:
     def __init__(self, model: nn.Module, shape: LlamaShape, max_ctx: int = 1280, pdl: bool = True, rank: int = 0, world_size: int = 1,
-                 group=None):
+                 group=None, allgather: Optional[str] = None):
         self.shape, self.max_ctx, self.pdl = shape, max_ctx, bool(pdl)
         self.rank, self.world, self.group = rank, world_size, group
+        # "p2p": all-gather fused into the GEMV epilogue over NVLink peer memory; "nccl": one ncclAllGather per linear
+        self.allgather = (allgather or os.environ.get("EETQ_B200_ALLGATHER", "p2p")) if world_size > 1 else "none"
         m = model.model
         dev = m.embed_tokens.weight.device
         self.device = dev
@@ -222,11 +225,21 @@ class W8A16LlamaDecoder:
         # decode-step buffers (device resident; the graph reads/writes these)
         self.token = torch.zeros(1, dtype=torch.int64, device=dev)
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.x = torch.zeros(H, dtype=dt, device=dev)
-        self.x2 = torch.zeros(H, dtype=dt, device=dev)
-        self.qkv = torch.zeros(3 * H, dtype=dt, device=dev)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)   # strictly increasing step counter (p2p flags)
+        self._p2p = None
+        if self.allgather == "p2p":
+            try:
+                self._setup_p2p(H, I, L, dt, dev)
+            except Exception as e:  # symmetric memory unavailable -> NCCL all-gather (still a GPU path, never a CPU one)
+                if rank == 0:
+                    print(f"[eetq_b200] p2p all-gather unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+                self.allgather, self._p2p = "nccl", None
+        if self._p2p is None:
+            self.x = torch.zeros(H, dtype=dt, device=dev)
+            self.x2 = torch.zeros(H, dtype=dt, device=dev)
+            self.qkv = torch.zeros(3 * H, dtype=dt, device=dev)
+            self.gu = torch.zeros(2 * I, dtype=dt, device=dev)
         self.attn = torch.zeros(H, dtype=dt, device=dev)
-        self.gu = torch.zeros(2 * I, dtype=dt, device=dev)
         self.xn = torch.zeros(1, H, dtype=dt, device=dev)
         self.logits = torch.zeros(1, shape.vocab, dtype=dt, device=dev)
         self._L = _cabi.lib()
@@ -235,6 +248,47 @@ class W8A16LlamaDecoder:
         self.tickets = torch.zeros(shape.heads, dtype=torch.int32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------------- p2p all-gather
+    def _setup_p2p(self, H, I, L, dt, dev):
+        """Activation buffers + flags in ONE symmetric-memory arena mapped into every rank (NVLink peer pointers)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        def rnd(n):
+            return (n + 255) // 256 * 256
+
+        nslot = 4 * L
+        sizes = [("x", H * 2), ("x2", H * 2), ("qkv", 3 * H * 2), ("gu", 2 * I * 2), ("flags", nslot * 8 * 4)]
+        offs, total = {}, 0
+        for name, nb in sizes:
+            offs[name] = total
+            total += rnd(nb)
+        arena = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        arena.zero_()
+        group = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(arena, group)
+        bases = [int(b) for b in hdl.buffer_ptrs]
+        assert len(bases) == self.world
+        view = lambda name, nb, dtype: arena[offs[name]:offs[name] + nb].view(dtype)
+        self.x, self.x2 = view("x", H * 2, dt), view("x2", H * 2, dt)
+        self.qkv, self.gu = view("qkv", 3 * H * 2, dt), view("gu", 2 * I * 2, dt)
+        flags = view("flags", nslot * 8 * 4, torch.int32)
+        self._p2p = dict(arena=arena, hdl=hdl, bases=bases, offs=offs, flags=flags, nslot=nslot,
+                         ticket=torch.zeros(1, dtype=torch.int32, device=dev), slot=0)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)   # every rank's flags are zero before anybody signals
+
+    def _p2p_args(self, y_full: torch.Tensor, lin, slot: int):
+        """ctypes arrays of peer pointers for output buffer `y_full` (a view into the arena) and flag slot `slot`."""
+        p = self._p2p
+        arena_base = p["arena"].data_ptr()
+        y_off = y_full.data_ptr() - arena_base + lin.n_begin * 2            # this rank's first row inside the buffer
+        f_off = p["offs"]["flags"] + (slot * 8) * 4
+        peer_y = (ctypes.c_uint64 * 8)(*[b + y_off for b in p["bases"]] + [0] * (8 - self.world))
+        peer_f = (ctypes.c_uint64 * 8)(*[b + f_off + self.rank * 4 for b in p["bases"]] + [0] * (8 - self.world))
+        local_flags = ctypes.c_void_p(arena_base + f_off)
+        return peer_y, peer_f, local_flags
 
     # ------------------------------------------------------------------------------------------------- construction
     @classmethod
@@ -250,6 +304,17 @@ class W8A16LlamaDecoder:
         off = lin.n_begin
         y = y_full[off:off + lin.n_local]
         res = None if residual_full is None else residual_full[off:off + lin.n_local]
+        if self._p2p is not None:
+            p = self._p2p
+            slot = p["slot"] % p["nslot"]
+            p["slot"] += 1
+            peer_y, peer_f, local_flags = self._p2p_args(y_full, lin, slot)
+            rc = self._L.eetq_b200_w8a16_gemv_fused_p2p(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), _vp(norm_w), float(self.shape.eps), xmode,
+                                                        _vp(res), lin.N, 1, lin.n_local, lin.K, _cabi.F16, self.world, peer_y, peer_f,
+                                                        local_flags, _vp(p["ticket"]), _vp(self.epoch), lin.N, 1 if self.pdl else 0,
+                                                        self._stream())
+            _cabi.check(rc, "eetq_b200_w8a16_gemv_fused_p2p")
+            return
         rc = self._L.eetq_b200_w8a16_gemv_fused(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), None, _vp(norm_w), float(self.shape.eps),
                                                 xmode, _vp(res), lin.N, _vp(y), lin.N, 1, lin.n_local, lin.K, _cabi.F16,
                                                 1 if self.pdl else 0, self._stream())
@@ -265,6 +330,9 @@ class W8A16LlamaDecoder:
         s, L, pdl = self.shape, self._L, 1 if self.pdl else 0
         H, I, D = s.hidden, s.inter, s.head_dim
         st = self._stream
+        if self._p2p is not None:
+            self._p2p["slot"] = 0
+            self.epoch.add_(1)   # one epoch per decode step; flags[slot] only ever increase
         _cabi.check(L.eetq_b200_decode_embed(_vp(self.embed), _vp(self.token), _vp(self.x), H, pdl, st()), "decode_embed")
         for li, w in enumerate(self.layers):
             self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1)
