@@ -19,6 +19,13 @@ GEMV_MAX_M = 8
 
 _lib: Optional[ctypes.CDLL] = None
 
+
+class GemvPhase(ctypes.Structure):
+    """eetq_b200_gemv_phase (include/eetq_b200.h)"""
+    _fields_ = [("x", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("w", ctypes.c_void_p), ("scales", ctypes.c_void_p),
+                ("y", ctypes.c_void_p), ("N", ctypes.c_int64), ("K", ctypes.c_int64), ("norm_weight", ctypes.c_void_p),
+                ("residual", ctypes.c_void_p), ("eps", ctypes.c_float), ("xmode", ctypes.c_int)]
+
 _c_i64 = ctypes.c_int64
 _c_vp = ctypes.c_void_p
 _c_int = ctypes.c_int
@@ -44,6 +51,7 @@ SIGNATURES = {
                                             _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
     "eetq_b200_w8a16_gemv_fused_p2p": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp, _c_i64, _c_i64, _c_i64,
                                                 _c_i64, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
+    "eetq_b200_w8a16_gemv_chain": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_int, _c_vp]),
     "eetq_b200_decode_embed": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "eetq_b200_decode_rmsnorm": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_int, _c_vp]),
     "eetq_b200_decode_attention_splits": (_c_i64, [_c_i64]),

@@ -76,6 +76,22 @@ struct GemvExtras {
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
                 int M, int64_t N, int64_t K, int dtype, const GemvExtras& ex, bool pdl, cudaStream_t stream);
 
+// one phase of a chained decode GEMV launch (M = 1, fp16); mirrors eetq_b200_gemv_phase in the public header
+struct GemvChainPhase {
+    const void* x;
+    int64_t ldx;
+    const void* w;
+    const void* scales;
+    void* y;
+    int64_t N;
+    int64_t K;
+    const void* norm_weight;
+    const void* residual;
+    float eps;
+    int xmode;
+};
+int launch_gemv_chain(const GemvChainPhase* phases, int nphases, unsigned* counters, const int* epoch, bool pdl, cudaStream_t stream);
+
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y,
                    int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes,

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(512) rmsnorm_kernel(const __half* __restrict__
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fused RoPE + KV-append + split-KV decode attention + split merge, one query token, ONE launch per layer.
-//   grid = (heads, splits), 128 threads, head_dim 128.  Each CTA owns <= 64 cache positions: thread (rowlane = t/16,
+//   grid = (heads, splits), 128 threads, head_dim 128.  CTA (h, s) owns the fixed cache rows [64 s, 64 s + 64): thread (rowlane = t/16,
 //   sub = t%16) holds 16-byte slices of 8 K rows and 8 V rows IN REGISTERS -- all 16 loads are issued up front (256 B in
 //   flight per thread), so the whole KV read of the layer is in flight at once and the kernel is a pure HBM stream.
 //   The CTA that owns the newest position rotates k, appends k/v to the cache and uses them from shared memory.
@@ -122,37 +122,37 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
     const int split   = blockIdx.y;
 
     pdl_launch_dependents();
-    // `pos` and cache rows < pos were written by earlier STEPS (complete long before this launch), so they may be read
-    // before the dependency wait: the KV stream of this layer overlaps the tail of the preceding qkv GEMV.
-    const int pos  = *pos_p;
-    const int L    = pos + 1;  // attend to positions [0, pos]
-    const int p0   = int((int64_t(split) * L) / splits);
-    const int p1   = int((int64_t(split + 1) * L) / splits);
-    const int n    = p1 - p0;                       // <= ATT_ROWS by construction of `splits`
-    const bool owns_new = (split == splits - 1);    // the last split always contains position pos
-    const int n_cache   = owns_new ? n - 1 : n;     // rows read from the cache
-
-    // issue every cache load first (K then V): 16 x 16 B per thread
+    // Split s owns the FIXED cache rows [64 s, 64 s + 64): the loads below need neither `pos` nor anything the preceding
+    // kernel produces (rows < pos were written by earlier STEPS; rows >= pos are masked out later), so the whole KV
+    // stream of the layer is in flight before the dependency wait and overlaps the tail of the q|k|v GEMV.
+    const int p0 = split * ATT_ROWS;
     uint4 kreg[8], vreg[8];
-    // cache layout [head][max_ctx][128]: the <= 64 rows of this CTA are ONE contiguous 16 KB block per tensor
     const __half* kbase = kcache + (int64_t(head) * max_ctx + p0) * ATT_D + sub * 8;
     const __half* vbase = vcache + (int64_t(head) * max_ctx + p0) * ATT_D + sub * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int j = i * 8 + rowlane;
-        kreg[i]     = (j < n_cache) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+        kreg[i]     = (p0 + j < max_ctx) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int j = i * 8 + rowlane;
-        vreg[i]     = (j < n_cache) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+        vreg[i]     = (p0 + j < max_ctx) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int pos = *pos_p;                            // written at the end of the previous step
+    const int L   = pos + 1;                           // attend to positions [0, pos]
+    const int n   = max(0, min(ATT_ROWS, L - p0));     // valid rows of this split
+    const bool owns_new = (pos >= p0) && (pos < p0 + ATT_ROWS);
+    float rope_c = 0.f, rope_s = 0.f;
+    if (t < ATT_D / 2) {
+        rope_c = __half2float(cos_t[int64_t(pos) * (ATT_D / 2) + t]);
+        rope_s = __half2float(sin_t[int64_t(pos) * (ATT_D / 2) + t]);
     }
     pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
 
     // RoPE of q (every CTA) and of the new k (owner CTA); HF rotate_half convention evaluated in fp16
     if (t < ATT_D / 2) {
-        const float c = __half2float(cos_t[int64_t(pos) * (ATT_D / 2) + t]);
-        const float s = __half2float(sin_t[int64_t(pos) * (ATT_D / 2) + t]);
+        const float c = rope_c, s = rope_s;
         const int a = head * ATT_D + t, b = a + ATT_D / 2;
         const float q0 = __half2float(qkv[a]), q1 = __half2float(qkv[b]);
         q_s[t]             = __half2float(__hadd(__float2half_rn(q0 * c), __float2half_rn(-q1 * s))) * scale;
@@ -376,6 +376,16 @@ int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200,
     return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl != 0, static_cast<cudaStream_t>(stream));
 }
 
+
+// Up to 4 dependent M=1 fp16 GEMVs in one launch (see w8a16_gemv_chain_kernel).  `phases` is an array of
+// eetq_b200_gemv_phase (layout-identical to eetq_b200::GemvChainPhase); counters: >= nphases-1 uint32, zero on first use,
+// PRIVATE to this chain position (they only ever increase); epoch: device int32 >= 1 that increases by 1 per launch.
+int eetq_b200_w8a16_gemv_chain(const void* phases, int nphases, void* counters, const void* epoch, int pdl, void* stream)
+{
+    EB_CHECK_ARG(phases && counters && epoch, "w8a16_gemv_chain: null pointer argument");
+    return launch_gemv_chain(static_cast<const GemvChainPhase*>(phases), nphases, static_cast<unsigned*>(counters),
+                             static_cast<const int*>(epoch), pdl != 0, static_cast<cudaStream_t>(stream));
+}
 
 // Column-sharded variant with the all-gather fused into the epilogue over NVLink peer memory (see GemvP2P in common.cuh).
 //   peer_y[r]    : rank r's copy of the FULL output vector, offset to this rank's first row (device-mapped peer pointer)

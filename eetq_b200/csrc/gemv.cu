@@ -568,6 +568,200 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG, LOW))
 }
 
 // =====================================================================================================================
+// Chained variant: up to 4 dependent decode GEMVs (o_proj -> gate|up -> down -> next layer's q|k|v) in ONE launch.
+// Between phases the CTAs meet at a grid barrier (monotonic counter, target = epoch * gridDim.x), but BEFORE waiting each
+// CTA has already issued the first two row groups of the next phase's weights (16 x 16-byte loads per thread, ~19 MB
+// chip-wide), so HBM keeps streaming across what used to be three kernel boundaries per layer.  M = 1, fp16.
+// =====================================================================================================================
+struct GemvPhase {
+    const __half* x;
+    int64_t ldx;
+    const uint8_t* w;
+    const __half* scales;
+    __half* y;
+    int N;
+    int K;
+    const __half* norm_weight;
+    const __half* residual;
+    float eps;
+    int xmode;
+};
+constexpr int kMaxChain = 4;
+struct GemvChain {
+    GemvPhase ph[kMaxChain];
+    int nphases;
+    unsigned* counters;   // one per phase boundary, never reset
+    const int* epoch;     // device step counter (>= 1), strictly increasing per launch of THIS chain
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int KITERS, int R>
+__device__ __forceinline__ void chain_phase(const GemvPhase& ph, bool first, const unsigned* wait_counter, unsigned target,
+                                            float (*red_smem)[kWarps])
+{
+    using T = __half;
+    const int tid     = threadIdx.x;
+    const int lane    = tid & 31;
+    const int warp    = tid >> 5;
+    const int K       = ph.K;
+    const int nchunks = K >> 4;
+    const int row_begin = int((int64_t(blockIdx.x) * ph.N) / gridDim.x);
+    const int row_end   = int((int64_t(blockIdx.x + 1) * ph.N) / gridDim.x);
+    const int nrows     = row_end - row_begin;
+    const int ngroups   = (nrows + R - 1) / R;
+
+    uint4 wb[2][R][KITERS];
+    auto load_group = [&](uint4 (&buf)[R][KITERS], int g) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = row_begin + g * R + r;
+#pragma unroll
+            for (int i = 0; i < KITERS; ++i) {
+                const int c = tid + i * kThreads;
+                if (row < row_end && c < nchunks)
+                    buf[r][i] = ldg_stream_128(ph.w + int64_t(row) * K + int64_t(c) * 16);
+                else
+                    buf[r][i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    };
+    // weights first (independent of the previous phase), then the dependency
+    if (ngroups > 0)
+        load_group(wb[0], 0);
+    if (ngroups > 1)
+        load_group(wb[1], 1);
+    if (first) {
+        pdl_wait_prior_grids();
+    }
+    else {
+        if (tid == 0) {
+            while (ld_acquire_gpu(wait_counter) < target) {
+            }
+        }
+        __syncthreads();
+    }
+
+    XSlice<T> xs[KITERS];
+#pragma unroll
+    for (int i = 0; i < KITERS; ++i) {
+        const int c = tid + i * kThreads;
+        if (c >= nchunks)
+            xs[i].zero();
+        else if (ph.xmode == GEMV_X_SILU_MUL)
+            xs[i].load_silu_mul(ph.x + int64_t(c) * 16, ph.x + K + int64_t(c) * 16);
+        else
+            xs[i].load(ph.x + int64_t(c) * 16);
+    }
+    if (ph.xmode == GEMV_X_RMSNORM) {
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < KITERS; ++i)
+            ss += xs[i].sumsq();
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1)
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0)
+            red_smem[0][warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < kWarps; ++wi)
+            tot += red_smem[0][wi];
+        const float r = rsqrtf(tot / float(K) + ph.eps);
+#pragma unroll
+        for (int i = 0; i < KITERS; ++i) {
+            const int c = tid + i * kThreads;
+            if (c < nchunks)
+                xs[i].apply_norm(r, ph.norm_weight + int64_t(c) * 16);
+        }
+    }
+    float so = 0.f;
+#pragma unroll
+    for (int i = 0; i < KITERS; ++i)
+        so += xs[i].sum;
+    const float xoff = -XSlice<T>::kOffset * so;
+
+    auto compute_group = [&](uint4 (&buf)[R][KITERS], int g) {
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float a = xoff;
+#pragma unroll
+            for (int i = 0; i < KITERS; ++i)
+                xs[i].dot(buf[r][i], a);
+            acc[r] = a;
+        }
+        const float tot = warp_reduce_rows<R>(acc, lane);
+        const int rid   = lane >> (5 - Log2<R>::v);
+        if ((lane & ((32 >> Log2<R>::v) - 1)) == 0)
+            gemv_partial[(g * R + rid) * kWarps + warp] = tot;
+    };
+    for (int g = 0; g < ngroups; g += 2) {
+        compute_group(wb[0], g);
+        if (g + 2 < ngroups)
+            load_group(wb[0], g + 2);
+        if (g + 1 < ngroups) {
+            compute_group(wb[1], g + 1);
+            if (g + 3 < ngroups)
+                load_group(wb[1], g + 3);
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < nrows; r += kThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < kWarps; ++wi)
+            s += gemv_partial[r * kWarps + wi];
+        const int n = row_begin + r;
+        __half o    = __float2half_rn(s * __half2float(ph.scales[n]));
+        if (ph.residual != nullptr)
+            o = __float2half_rn(__half2float(o) + __half2float(ph.residual[n]));
+        ph.y[n] = o;
+    }
+}
+
+template <int KI>
+struct ChainR {
+    static constexpr int v = KI == 1 ? 8 : (KI == 2 ? 4 : 2);
+};
+
+// KI0..KI3: K-chunk iterations (ceil(K/4096)) of each phase, 0 = phase absent.  Fully unrolled so every phase indexes the
+// kernel-parameter struct statically (no local-memory copy) and gets its own register allocation.
+template <int KI0, int KI1, int KI2, int KI3>
+__global__ void __launch_bounds__(kThreads, 2) w8a16_gemv_chain_kernel(const __grid_constant__ GemvChain c)
+{
+    __shared__ float red_smem[1][kWarps];
+    pdl_launch_dependents();
+    const unsigned target = unsigned(*c.epoch) * gridDim.x;
+    auto arrive = [&](int p) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(c.counters + p, 1u);
+        }
+    };
+    chain_phase<KI0, ChainR<KI0>::v>(c.ph[0], true, c.counters, target, red_smem);
+    if constexpr (KI1 > 0) {
+        arrive(0);
+        chain_phase<KI1, ChainR<KI1>::v>(c.ph[1], false, c.counters + 0, target, red_smem);
+    }
+    if constexpr (KI2 > 0) {
+        arrive(1);
+        chain_phase<KI2, ChainR<KI2>::v>(c.ph[2], false, c.counters + 1, target, red_smem);
+    }
+    if constexpr (KI3 > 0) {
+        arrive(2);
+        chain_phase<KI3, ChainR<KI3>::v>(c.ph[3], false, c.counters + 2, target, red_smem);
+    }
+}
+
+// =====================================================================================================================
 // TMA-streamed variant (default): the CTA's rows are ONE contiguous byte range of the b200 layout, so a single
 // producer thread streams it with cp.async.bulk (TMA 1-D) into a shared-memory ring (~96 KB/CTA, one CTA per SM) and
 // runs AHEAD of the consumers -- across stages and, under programmatic dependent launch, across kernels: the next
@@ -947,6 +1141,61 @@ int dispatch_m(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     }
 }
 
+int launch_gemv_chain_impl(const GemvChain& chain, int max_rows_hint, bool pdl, cudaStream_t stream)
+{
+    const DeviceInfo& di = device_info();
+    if (!di.ok) {
+        set_error("gemv_chain: device query failed");
+        return EETQ_B200_ECUDA;
+    }
+    const int grid = di.sm_count * 2;
+    int max_rows   = 0;
+    for (int p = 0; p < chain.nphases; ++p) {
+        const int rows = (chain.ph[p].N + grid - 1) / grid;
+        if (rows > max_rows) max_rows = rows;
+        if (chain.ph[p].N < grid) {
+            set_error("gemv_chain: phase %d (N=%d) smaller than the grid", p, chain.ph[p].N);
+            return EETQ_B200_EINVAL;
+        }
+    }
+    int ki[kMaxChain] = {0, 0, 0, 0};
+    for (int p = 0; p < chain.nphases; ++p)
+        ki[p] = ((chain.ph[p].K >> 4) + kThreads - 1) / kThreads;
+    // instantiated shapes: Llama-7B-like (hidden <= 4096, 8192 < inter <= 12288): o -> gate|up -> down [-> q|k|v]
+    void (*kernel)(const GemvChain) = nullptr;
+    if (ki[0] == 1 && ki[1] == 1 && ki[2] == 3 && ki[3] == 1)
+        kernel = w8a16_gemv_chain_kernel<1, 1, 3, 1>;
+    else if (ki[0] == 1 && ki[1] == 1 && ki[2] == 3 && ki[3] == 0)
+        kernel = w8a16_gemv_chain_kernel<1, 1, 3, 0>;
+    else if (ki[0] == 1 && ki[1] == 1 && ki[2] == 1 && ki[3] == 1)
+        kernel = w8a16_gemv_chain_kernel<1, 1, 1, 1>;
+    else if (ki[0] == 1 && ki[1] == 1 && ki[2] == 1 && ki[3] == 0)
+        kernel = w8a16_gemv_chain_kernel<1, 1, 1, 0>;
+    if (kernel == nullptr) {
+        set_error("gemv_chain: K-iteration pattern (%d,%d,%d,%d) is not instantiated", ki[0], ki[1], ki[2], ki[3]);
+        return EETQ_B200_EINVAL;
+    }
+    (void)max_rows_hint;
+    const size_t smem = size_t(((max_rows + 7) / 8) * 8) * kWarps * sizeof(float);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim          = dim3(unsigned(grid));
+    cfg.blockDim         = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream           = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, chain);
+    count_launch();
+    if (e != cudaSuccess) {
+        set_error("gemv_chain launch failed: %s", cudaGetErrorString(e));
+        return EETQ_B200_ECUDA;
+    }
+    return EETQ_B200_OK;
+}
+
 }  // namespace
 
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
@@ -967,6 +1216,25 @@ int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales,
     }
     set_error("gemv: unsupported activation dtype %d", dtype);
     return EETQ_B200_EINVAL;
+}
+
+int launch_gemv_chain(const GemvChainPhase* phases, int nphases, unsigned* counters, const int* epoch, bool pdl, cudaStream_t stream)
+{
+    if (nphases < 1 || nphases > kMaxChain) {
+        set_error("gemv_chain: nphases must be in [1, %d]", kMaxChain);
+        return EETQ_B200_EINVAL;
+    }
+    GemvChain c{};
+    for (int p = 0; p < nphases; ++p) {
+        const GemvChainPhase& s = phases[p];
+        c.ph[p] = GemvPhase{static_cast<const __half*>(s.x), s.ldx, reinterpret_cast<const uint8_t*>(s.w),
+                            static_cast<const __half*>(s.scales), static_cast<__half*>(s.y), int(s.N), int(s.K),
+                            static_cast<const __half*>(s.norm_weight), static_cast<const __half*>(s.residual), s.eps, s.xmode};
+    }
+    c.nphases  = nphases;
+    c.counters = counters;
+    c.epoch    = epoch;
+    return launch_gemv_chain_impl(c, 0, pdl, stream);
 }
 
 }  // namespace eetq_b200

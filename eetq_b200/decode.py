@@ -194,7 +194,7 @@ class _ShardedLinear:
 
 class W8A16LlamaDecoder:
     def __init__(self, model: nn.Module, shape: LlamaShape, max_ctx: int = 1280, pdl: bool = True, rank: int = 0, world_size: int = 1,
-                 group=None, allgather: Optional[str] = None):
+                 group=None, allgather: Optional[str] = None, chain: Optional[bool] = None):
         self.shape, self.max_ctx, self.pdl = shape, max_ctx, bool(pdl)
         self.rank, self.world, self.group = rank, world_size, group
         # "p2p": all-gather fused into the GEMV epilogue over NVLink peer memory; "nccl": one ncclAllGather per linear
@@ -240,6 +240,11 @@ class W8A16LlamaDecoder:
             self.qkv = torch.zeros(3 * H, dtype=dt, device=dev)
             self.gu = torch.zeros(2 * I, dtype=dt, device=dev)
         self.attn = torch.zeros(H, dtype=dt, device=dev)
+        # single GPU: o_proj -> gate|up -> down -> next q|k|v run as ONE chained launch per layer (grid barriers inside)
+        if chain is None:
+            chain = os.environ.get("EETQ_B200_CHAIN", "1") != "0"
+        self.chain = bool(chain) and world_size == 1
+        self.chain_counters = torch.zeros(L, 4, dtype=torch.int32, device=dev)
         self.xn = torch.zeros(1, H, dtype=dt, device=dev)
         self.logits = torch.zeros(1, shape.vocab, dtype=dt, device=dev)
         self._L = _cabi.lib()
@@ -334,15 +339,40 @@ class W8A16LlamaDecoder:
             self._p2p["slot"] = 0
             self.epoch.add_(1)   # one epoch per decode step; flags[slot] only ever increase
         _cabi.check(L.eetq_b200_decode_embed(_vp(self.embed), _vp(self.token), _vp(self.x), H, pdl, st()), "decode_embed")
-        for li, w in enumerate(self.layers):
-            self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1)
+        def attention(li):
             _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
                                                      _vp(self.vcache[li]), _vp(self.partial), _vp(self.tickets), _vp(self.attn), H, D,
                                                      self.max_ctx, pdl, st()), "decode_attention")
-            # x2 = x + o_proj(attn); x = x2 + down(silu(gate) * up)   (ping-pong so no kernel reads what it writes)
-            self._gemv(self.attn, H, w["o"], self.x2, residual_full=self.x)
-            self._gemv(self.x2, H, w["gu"], self.gu, norm_w=w["ln2"], xmode=1)
-            self._gemv(self.gu, 2 * I, w["down"], self.x, xmode=2, residual_full=self.x2)
+
+        if self.chain:
+            nl = len(self.layers)
+            self.epoch.add_(1)
+            self._gemv(self.x, H, self.layers[0]["qkv"], self.qkv, norm_w=self.layers[0]["ln1"], xmode=1)
+            for li, w in enumerate(self.layers):
+                attention(li)
+                # x2 = x + o_proj(attn); gu = gate|up(norm(x2)); x = x2 + down(silu(gate)*up); qkv = q|k|v(norm(x)) of the next layer
+                phases = [
+                    (self.attn, H, w["o"], self.x2, None, self.x, 0),
+                    (self.x2, H, w["gu"], self.gu, w["ln2"], None, 1),
+                    (self.gu, 2 * I, w["down"], self.x, None, self.x2, 2),
+                ]
+                if li + 1 < nl:
+                    nxt = self.layers[li + 1]
+                    phases.append((self.x, H, nxt["qkv"], self.qkv, nxt["ln1"], None, 1))
+                arr = (_cabi.GemvPhase * len(phases))()
+                for i, (xin, ldx, lin, y, nw, res, xmode) in enumerate(phases):
+                    arr[i] = _cabi.GemvPhase(xin.data_ptr(), ldx, lin.w.data_ptr(), lin.scales.data_ptr(), y.data_ptr(), lin.N, lin.K,
+                                             0 if nw is None else nw.data_ptr(), 0 if res is None else res.data_ptr(), float(s.eps), xmode)
+                _cabi.check(L.eetq_b200_w8a16_gemv_chain(ctypes.byref(arr), len(phases), _vp(self.chain_counters[li]), _vp(self.epoch),
+                                                          pdl, st()), "eetq_b200_w8a16_gemv_chain")
+        else:
+            for li, w in enumerate(self.layers):
+                self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1)
+                attention(li)
+                # x2 = x + o_proj(attn); x = x2 + down(silu(gate) * up)   (ping-pong so no kernel reads what it writes)
+                self._gemv(self.attn, H, w["o"], self.x2, residual_full=self.x)
+                self._gemv(self.x2, H, w["gu"], self.gu, norm_w=w["ln2"], xmode=1)
+                self._gemv(self.gu, 2 * I, w["down"], self.x, xmode=2, residual_full=self.x2)
         _cabi.check(L.eetq_b200_decode_rmsnorm(_vp(self.x), _vp(self.norm_w), _vp(self.xn), 1, H, float(s.eps), pdl, st()), "decode_rmsnorm")
         torch.matmul(self.xn, self.lm_head_w.t(), out=self.logits)       # fp16 lm_head (library GEMV; not quantised)
         self.token.copy_(torch.argmax(self.logits, dim=-1))               # greedy

@@ -146,6 +146,24 @@ int eetq_b200_w8a16_gemm_host(const void* x_host, void* x_dev, const int8_t* w_b
 int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
                                const void* norm_weight, float eps, int xmode, const void* residual, int64_t ldr, void* y,
                                int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, int pdl, void* stream);
+/* Up to 4 DEPENDENT decode GEMVs (M = 1, fp16; e.g. o_proj -> gate|up -> down -> next layer's q|k|v) in ONE launch:
+ * the CTAs meet at a grid barrier between phases but issue the next phase's first weight loads before waiting, so the
+ * HBM stream does not stop at what would otherwise be kernel boundaries.  counters: nphases-1 uint32 private to this call
+ * site, zero on first use (they only increase); epoch: device int32 >= 1 that increases by exactly 1 per launch. */
+typedef struct eetq_b200_gemv_phase {
+    const void* x;            /* activation [K] (or [2K] for xmode 2) */
+    int64_t ldx;
+    const void* w;            /* b200 layout, N*K bytes */
+    const void* scales;       /* [N] fp16 */
+    void* y;                  /* [N] fp16 */
+    int64_t N, K;
+    const void* norm_weight;  /* xmode 1 */
+    const void* residual;     /* [N] or NULL */
+    float eps;
+    int xmode;                /* 0 plain, 1 RMSNorm on load, 2 silu(x[:K]) * x[K:2K] */
+} eetq_b200_gemv_phase;
+int eetq_b200_w8a16_gemv_chain(const void* phases, int nphases, void* counters, const void* epoch, int pdl, void* stream);
+
 /* Column-sharded decode GEMV with the activation all-gather FUSED into the epilogue over NVLink peer memory
  * (one all-gather per sharded linear).  Rank r owns rows [r*N/P, (r+1)*N/P) of the linear; every
  * rank stores its slice straight into all ranks' copies of the output vector (peer-mapped symmetric memory), the last

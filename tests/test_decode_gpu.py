@@ -78,15 +78,27 @@ def test_decode_matches_torch_forward(cuda):
         assert int(dec.pos.item()) == i + 1
 
 
-def test_pdl_and_plain_launch_agree(cuda):
+def test_pdl_chain_and_plain_launch_agree(cuda):
     model = LlamaSkeleton(SMALL, device=cuda, seed=4, std=0.05)
     eetq_b200.eet_quantize(model)
     prompt = torch.randint(0, SMALL.vocab, (16,), device=cuda)
     outs = []
-    for pdl in (True, False):
-        dec = W8A16LlamaDecoder.from_model(model, max_ctx=64, pdl=pdl)
+    for pdl, chain in ((True, True), (False, True), (True, False), (False, False)):
+        dec = W8A16LlamaDecoder.from_model(model, max_ctx=64, pdl=pdl, chain=chain)
         outs.append(dec.generate(prompt, 12))
-    assert outs[0] == outs[1]
+    assert all(o == outs[0] for o in outs[1:])
+
+
+def test_chain_matches_unchained_on_7b_shapes(cuda):
+    """One Llama-2-7B-shaped layer pair (K patterns 4096/4096/11008/4096): chained launch == four separate launches."""
+    from eetq_b200.decode import LlamaShape
+    shape = LlamaShape(hidden=4096, inter=11008, layers=2, heads=32, vocab=512, name="7b-2layer")
+    model = LlamaSkeleton(shape, device=cuda, seed=9)
+    eetq_b200.eet_quantize(model)
+    prompt = torch.randint(0, shape.vocab, (70,), device=cuda)
+    a = W8A16LlamaDecoder.from_model(model, max_ctx=160, chain=True).generate(prompt, 20)
+    b = W8A16LlamaDecoder.from_model(model, max_ctx=160, chain=False).generate(prompt, 20)
+    assert a == b
 
 
 def test_step_host_roundtrip(cuda):
@@ -105,4 +117,5 @@ def test_step_host_roundtrip(cuda):
         a.copy_(b)
     dec2 = W8A16LlamaDecoder.from_model(model, max_ctx=64)
     assert dec2.generate(prompt, 6)[1:] == seq
-    assert dec.launches_per_step == 1 + SMALL.layers * 5 + 1   # embed + per layer (4 GEMV + fused attention) + final norm
+    # chained: embed + first q|k|v + per layer (fused attention + one chained GEMV launch) + final norm
+    assert dec.launches_per_step == 1 + 1 + SMALL.layers * 2 + 1
