@@ -117,5 +117,5 @@ def test_step_host_roundtrip(cuda):
         a.copy_(b)
     dec2 = W8A16LlamaDecoder.from_model(model, max_ctx=64)
     assert dec2.generate(prompt, 6)[1:] == seq
-    # chained: embed + first q|k|v + per layer (fused attention + one chained GEMV launch) + final norm
-    assert dec.launches_per_step == 1 + 1 + SMALL.layers * 2 + 1
+    # embed + per layer (4 fused GEMVs + 1 fused attention) + final norm
+    assert dec.launches_per_step == 1 + SMALL.layers * 5 + 1
