@@ -16,7 +16,8 @@
 //
 // Warp roles (320 threads):  warp 0 = TMA producer | warp 1 = tcgen05.mma issuer + TMEM alloc/dealloc |
 //                            warps 2..9 = dequantisers (two groups of 4 on alternating k-blocks), then epilogue
-// Pipelines (mbarrier):      full/empty[STAGES] : TMA  <-> {dequant (int8 tile), MMA (activation tile)}
+// Pipelines (mbarrier):      wfull/wempty[WS]   : TMA  <-> dequant   (int8, 256 k-bytes per stage = 4 MMA k-blocks)
+//                            xfull/xempty[XS]   : TMA  <-> MMA       (activation tile, 64 k)
 //                            a_full/a_empty[4]  : dequant <-> MMA (fp16 A tile)
 //                            tmem_full          : MMA -> epilogue
 //
@@ -52,11 +53,20 @@ constexpr int TC_THREADS   = 64 + DQ_THREADS;  // warp 0 TMA, warp 1 MMA, 8 dequ
 constexpr int W8_TILE      = BLOCK_N * BLOCK_K;       // 8192 B of int8
 constexpr int A_TILE       = BLOCK_N * BLOCK_K * 2;   // 16384 B of fp16/bf16
 
-__host__ __device__ constexpr int stages_for(int bt) { return bt >= 256 ? 3 : (bt >= 128 ? 5 : 8); }
+// The int8 weights are staged 256 k-bytes at a time (two 128-byte-wide, 128B-swizzled TMA boxes per stage): the b200
+// layout is row-major, so a 64-byte-wide box would touch 128 DRAM pages for 8 KB -- 256 contiguous bytes per row is the
+// widest box TMA allows for 1-byte elements.  Each weight stage therefore feeds 4 consecutive 64-k MMA blocks; the
+// activation tiles keep their own (64-k) stage ring.
+constexpr int W_SUB          = 4;                       // 64-k sub-blocks per weight stage
+constexpr int W_STAGE        = W_SUB * W8_TILE;         // 32 KB
+constexpr int W_HALF         = BLOCK_N * 128;           // one 128-byte-wide swizzled box = 16 KB
+__host__ __device__ constexpr int w_stages_for(int bt) { return bt >= 256 ? 2 : (bt >= 64 ? 3 : 4); }
+__host__ __device__ constexpr int x_stages_for(int bt) { return bt >= 256 ? 2 : (bt >= 128 ? 3 : (bt >= 64 ? 4 : 6)); }
 __host__ __device__ constexpr int x_tile_bytes(int bt) { return bt * BLOCK_K * 2; }
 __host__ __device__ constexpr int smem_bytes_for(int bt)
 {
-    return 1024 /*alignment slack*/ + stages_for(bt) * (W8_TILE + x_tile_bytes(bt)) + NUM_A_STAGES * A_TILE + 256 /*barriers*/;
+    return 1024 /*alignment slack*/ + w_stages_for(bt) * W_STAGE + x_stages_for(bt) * x_tile_bytes(bt) + NUM_A_STAGES * A_TILE
+           + 512 /*barriers*/;
 }
 __host__ __device__ constexpr int tmem_cols_for(int bt) { return bt < 32 ? 32 : bt; }
 
@@ -223,7 +233,8 @@ template <typename T, int BT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     w8a16_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p)
 {
-    constexpr int STAGES     = stages_for(BT);
+    constexpr int WS         = w_stages_for(BT);
+    constexpr int XS         = x_stages_for(BT);
     constexpr int X_TILE     = x_tile_bytes(BT);
     constexpr int TMEM_COLS  = tmem_cols_for(BT);
     constexpr bool SCALE_IN_A = DTypeOf<T>::value == EETQ_B200_F16;
@@ -231,13 +242,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t w8_base   = smem_base;                                   // STAGES x 8 KB
-    const uint32_t x_base    = w8_base + STAGES * W8_TILE;                   // STAGES x X_TILE
-    const uint32_t a_base    = x_base + STAGES * X_TILE;                     // 2 x 16 KB
+    const uint32_t w8_base   = smem_base;                                   // WS x 32 KB (two swizzled 16 KB halves each)
+    const uint32_t x_base    = w8_base + WS * W_STAGE;                       // XS x X_TILE
+    const uint32_t a_base    = x_base + XS * X_TILE;                         // 4 x 16 KB
     const uint32_t bar_base  = a_base + NUM_A_STAGES * A_TILE;
-    const uint32_t full_bar  = bar_base;                 // STAGES x 8
-    const uint32_t empty_bar = full_bar + STAGES * 8;    // STAGES x 8
-    const uint32_t afull_bar = empty_bar + STAGES * 8;   // 2 x 8
+    const uint32_t wfull_bar  = bar_base;                 // WS x 8
+    const uint32_t wempty_bar = wfull_bar + WS * 8;       // WS x 8
+    const uint32_t xfull_bar  = wempty_bar + WS * 8;      // XS x 8
+    const uint32_t xempty_bar = xfull_bar + XS * 8;       // XS x 8
+    const uint32_t afull_bar  = xempty_bar + XS * 8;      // 4 x 8
     const uint32_t aempty_bar = afull_bar + NUM_A_STAGES * 8;
     const uint32_t tfull_bar = aempty_bar + NUM_A_STAGES * 8;
     const uint32_t tmem_holder = tfull_bar + 8;
@@ -259,9 +272,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_x);
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar + 8 * s, 1);
-            mbar_init(empty_bar + 8 * s, 1);
+        for (int s = 0; s < WS; ++s) {
+            mbar_init(wfull_bar + 8 * s, 1);
+            mbar_init(wempty_bar + 8 * s, DQ_WARPS);  // every dequant warp reads two sub-blocks of each weight stage
+        }
+        for (int s = 0; s < XS; ++s) {
+            mbar_init(xfull_bar + 8 * s, 1);
+            mbar_init(xempty_bar + 8 * s, 1);
         }
         for (int a = 0; a < NUM_A_STAGES; ++a) {
             mbar_init(afull_bar + 8 * a, DQ_WARPS / DQ_GROUPS);  // one elected arrive per warp of the owning group
@@ -284,13 +301,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // ============================================================== TMA producer
         if (lane == 0) {
             for (int it = 0; it < num_kb; ++it) {
-                const int s        = it % STAGES;
-                const uint32_t ph  = (it / STAGES) & 1;
-                mbar_wait(empty_bar + 8 * s, ph ^ 1);
-                mbar_arrive_expect_tx(full_bar + 8 * s, W8_TILE + X_TILE);
                 const int k0 = (kb_begin + it) * BLOCK_K;
-                tma_load_2d(w8_base + s * W8_TILE, &map_w, full_bar + 8 * s, k0, n_tile * BLOCK_N);
-                tma_load_2d(x_base + s * X_TILE, &map_x, full_bar + 8 * s, k0, t_tile * BT);
+                if ((it % W_SUB) == 0) {
+                    const int wi       = it / W_SUB;
+                    const int ws       = wi % WS;
+                    const uint32_t wph = (wi / WS) & 1;
+                    mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
+                    mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
+                    // k beyond K is zero-filled by TMA (and never converted: sub-blocks past num_kb are skipped)
+                    tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, k0, n_tile * BLOCK_N);
+                    tma_load_2d(w8_base + ws * W_STAGE + W_HALF, &map_w, wfull_bar + 8 * ws, k0 + 128, n_tile * BLOCK_N);
+                }
+                const int xs       = it % XS;
+                const uint32_t xph = (it / XS) & 1;
+                mbar_wait(xempty_bar + 8 * xs, xph ^ 1);
+                mbar_arrive_expect_tx(xfull_bar + 8 * xs, X_TILE);
+                tma_load_2d(x_base + xs * X_TILE, &map_x, xfull_bar + 8 * xs, k0, t_tile * BT);
             }
         }
     }
@@ -298,11 +324,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // ============================================================== MMA issuer (one thread)
         if (lane == 0) {
             for (int it = 0; it < num_kb; ++it) {
-                const int s       = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+                const int s       = it % XS;
+                const uint32_t ph = (it / XS) & 1;
                 const int a       = it % NUM_A_STAGES;
                 const uint32_t aph = (it / NUM_A_STAGES) & 1;
-                mbar_wait(full_bar + 8 * s, ph);      // activation tile landed
+                mbar_wait(xfull_bar + 8 * s, ph);     // activation tile landed
                 mbar_wait(afull_bar + 8 * a, aph);    // dequantised weight tile written
                 tc_fence_after();
                 const uint64_t a_desc = make_kmajor_sw128_desc(a_base + a * A_TILE);
@@ -312,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (>>4) address field
                     umma_f16(tmem_base, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), IDESC, (it > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(empty_bar + 8 * s);     // frees the TMA stage (int8 tile was consumed before a_full)
+                umma_commit(xempty_bar + 8 * s);    // frees the activation stage
                 umma_commit(aempty_bar + 8 * a);    // frees the A stage
             }
             umma_commit(tfull_bar);                  // accumulator complete
@@ -341,21 +367,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
         }
         for (int it = grp; it < num_kb; it += DQ_GROUPS) {
-            const int s       = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            const int a       = it % NUM_A_STAGES;
+            const int wi       = it / W_SUB;
+            const int sub_k    = it % W_SUB;          // which 64-k slice of the 256-k weight stage
+            const int ws       = wi % WS;
+            const uint32_t wph = (wi / WS) & 1;
+            const int a        = it % NUM_A_STAGES;
             const uint32_t aph = (it / NUM_A_STAGES) & 1;
-            mbar_wait(full_bar + 8 * s, ph);          // int8 tile landed
-            const uint8_t* w8 = smem_gen + (w8_base - smem_base) + s * W8_TILE;
+            mbar_wait(wfull_bar + 8 * ws, wph);       // int8 stage landed
+            // stage = two [128 rows][128 B] halves, 128B-swizzled: 16-byte chunk index ^= (row & 7)
+            const uint8_t* w8 = smem_gen + (w8_base - smem_base) + ws * W_STAGE + (sub_k >> 1) * W_HALF;
             uint8_t* at       = smem_gen + (a_base - smem_base) + a * A_TILE;
             uint4 in[CHUNKS_PER_THREAD];
 #pragma unroll
-            for (int j = 0; j < CHUNKS_PER_THREAD; ++j)
-                in[j] = *reinterpret_cast<const uint4*>(w8 + (gt + GROUP_THREADS * j) * 16);
+            for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
+                const int c   = gt + GROUP_THREADS * j;
+                const int row = c >> 2;
+                const int ci  = (sub_k & 1) * 4 + (c & 3);  // chunk within the 128-byte row of this half
+                in[j] = *reinterpret_cast<const uint4*>(w8 + row * 128 + ((ci ^ (row & 7)) << 4));
+            }
             mbar_wait(aempty_bar + 8 * a, aph ^ 1);   // A stage free (the MMA that read it has completed)
 #pragma unroll
             for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
-                const int c   = gt + GROUP_THREADS * j;  // 16-byte chunk index in the [128][64 B] int8 tile
+                const int c   = gt + GROUP_THREADS * j;  // 16-byte chunk index in the [128][64 B] slice
                 const int row = c >> 2;
                 const int kc  = c & 3;
                 uint4 o0, o1;
@@ -367,8 +400,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
             fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0)
+            if (lane == 0) {
                 mbar_arrive(afull_bar + 8 * a);
+                // the int8 bytes have been consumed (converted): after this group's last sub-block of the weight stage
+                // (sub-blocks 2 / 3, or its final k-block) hand the stage back to the TMA producer -- once per warp
+                if (sub_k >= W_SUB - DQ_GROUPS || it + DQ_GROUPS >= num_kb)
+                    mbar_arrive(wempty_bar + 8 * ws);
+            }
         }
 
         // ---------------------------------------------------------- epilogue
@@ -631,8 +669,8 @@ int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scal
         cfg.splits = 1;
     }
     CUtensorMap map_w, map_x;
-    if (int rc = get_tensor_map(w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 100, uint64_t(K), uint64_t(N), uint64_t(K), BLOCK_K, BLOCK_N,
-                                CU_TENSOR_MAP_SWIZZLE_NONE, &map_w))
+    if (int rc = get_tensor_map(w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 100, uint64_t(K), uint64_t(N), uint64_t(K), 128, BLOCK_N,
+                                CU_TENSOR_MAP_SWIZZLE_128B, &map_w))
         return rc;
     const CUtensorMapDataType xdt = dtype == EETQ_B200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (int rc = get_tensor_map(x, xdt, dtype, uint64_t(K), uint64_t(M), uint64_t(ldx) * 2, BLOCK_K, uint32_t(cfg.bt),
