@@ -26,8 +26,9 @@
 // match it up to fp32 summation order.  bf16 (extension): A = bf16(q) exactly, scale applied in the fp32 epilogue.
 //
 // Small M is HBM-bound and N/128 tiles do not fill 148 SMs, so K is split over `splits` CTAs per tile; partial
-// tiles go through an fp32 workspace and the LAST CTA to arrive reduces them in split order (deterministic)
-// and resets the tile counter, so the workspace needs zeroing only once (the reference disables split-K
+// tiles go through an fp32 workspace; the `splits` CTAs of a tile meet at a counter and each reduces its share of
+// the token columns in split order (deterministic); the last to leave resets the counters, so the workspace needs
+// zeroing only once (the reference disables split-K
 // altogether by passing a null workspace, fpA_intB_gemm_wrapper.cu:169-170).
 //
 // Roofline: bytes = K*N + 2N + 2MK + 2MN, flops = 2MNK; HBM-bound for M <~ 140, tensor-bound above.
@@ -61,7 +62,7 @@ constexpr int W_SUB          = 4;                       // 64-k sub-blocks per w
 constexpr int W_STAGE        = W_SUB * W8_TILE;         // 32 KB
 constexpr int W_HALF         = BLOCK_N * 128;           // one 128-byte-wide swizzled box = 16 KB
 __host__ __device__ constexpr int w_stages_for(int bt) { return bt >= 256 ? 2 : (bt >= 64 ? 3 : 4); }
-__host__ __device__ constexpr int x_stages_for(int bt) { return bt >= 256 ? 2 : (bt >= 128 ? 3 : (bt >= 64 ? 4 : 6)); }
+__host__ __device__ constexpr int x_stages_for(int bt) { return bt >= 256 ? 3 : (bt >= 128 ? 3 : (bt >= 64 ? 4 : 6)); }
 __host__ __device__ constexpr int x_tile_bytes(int bt) { return bt * BLOCK_K * 2; }
 __host__ __device__ constexpr int smem_bytes_for(int bt)
 {
@@ -457,28 +458,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
             __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
+            // All `splits` CTAs of this tile are co-resident (grid <= 148 CTAs, one per SM): meet at an arrive counter, then
+            // EVERY CTA reduces its own 1/splits share of the token columns (in split order -> deterministic) instead of
+            // leaving one CTA to walk the whole tile through a chain of dependent L2 round trips.
+            int* arrive = p.tile_counters + tile_id;
+            int* depart = p.tile_counters + 512 + tile_id;
             if (dt == 0) {
-                const int old = atomicAdd(p.tile_counters + tile_id, 1);
-                const int last = (old == p.splits - 1) ? 1 : 0;
-                if (last)
-                    p.tile_counters[tile_id] = 0;  // leave the workspace clean for the next call
-                *reinterpret_cast<volatile int*>(smem_gen + (flag_holder - smem_base)) = last;
+                atomicAdd(arrive, 1);
+                while (*reinterpret_cast<volatile int*>(arrive) < p.splits) {
+                }
+                __threadfence();
             }
             asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
-            const int is_last = *reinterpret_cast<volatile int*>(smem_gen + (flag_holder - smem_base));
-            if (is_last) {
-                __threadfence();
-                for (int c = col_begin; c < col_end; ++c) {
-                    const int t = t_tile * BT + c;
-                    if (t >= p.M)
-                        break;
+            const int cs      = BT / p.splits;                 // columns reduced by this CTA (splits is a power of two <= 8)
+            const int my_c0   = split * cs;
+            const int per_grp = (cs >= 2) ? cs / 2 : cs;       // the two warps of a lane quadrant share the columns
+            const int c_begin = my_c0 + ((cs >= 2) ? half_i * per_grp : 0);
+            const int c_end   = (cs >= 2 || half_i == 0) ? c_begin + per_grp : c_begin;
+            const int64_t tile_stride = int64_t(gridDim.x) * gridDim.y * (BT * BLOCK_N);
+            const float* base = p.partials + int64_t(tile_id) * (BT * BLOCK_N) + quad * 32 + lane;
+            for (int c = c_begin; c < c_end; c += 4) {
+                float v[4][8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int sp = 0; sp < 8; ++sp)
+                        v[u][sp] = (sp < p.splits && c + u < c_end) ? __ldcg(base + sp * tile_stride + (c + u) * BLOCK_N) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
                     float acc = 0.f;
-                    for (int sp = 0; sp < p.splits; ++sp) {
-                        const float* part = p.partials + (int64_t(sp) * (gridDim.x * gridDim.y) + tile_id) * (BT * BLOCK_N);
-                        acc += __ldcg(part + c * BLOCK_N + quad * 32 + lane);
-                    }
-                    if (n_ok)
+#pragma unroll
+                    for (int sp = 0; sp < 8; ++sp)
+                        acc += v[u][sp];
+                    const int t = t_tile * BT + c + u;
+                    if (c + u < c_end && n_ok && t < p.M)
                         y[int64_t(t) * p.ldy + n] = from_float<T>(acc * scale_f + bias_f);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
+            if (dt == 0) {
+                // last CTA to leave resets both counters so the workspace stays clean for the next call
+                if (atomicAdd(depart, 1) == p.splits - 1) {
+                    *reinterpret_cast<volatile int*>(arrive) = 0;
+                    *reinterpret_cast<volatile int*>(depart) = 0;
                 }
             }
         }
@@ -592,6 +614,7 @@ TcConfig choose_config(int64_t M, int64_t N, int64_t K)
     if (s > max_s) s = max_s;
     if (s > 8) s = 8;
     if (s < 1) s = 1;
+    while (s & (s - 1)) --s;  // power of two: every split CTA reduces an equal share of the token columns
     c.splits = s;
     return c;
 }
