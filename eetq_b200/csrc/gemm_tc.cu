@@ -14,8 +14,9 @@
 //      B = activation tile          [BT tokens   x 64 k]  fp16/bf16, K-major, 128B-swizzled   (TMA straight from x)
 //      D = fp32 accumulator in TMEM: lane = feature, column = token   (UMMA M = 128, N = BT, K = 16)
 //
-// Warp roles (320 threads):  warp 0 = TMA producer | warp 1 = tcgen05.mma issuer + TMEM alloc/dealloc |
-//                            warps 2..9 = dequantisers (two groups of 4 on alternating k-blocks), then epilogue
+// Warp roles (352 threads):  warp 0 = weight TMA producer | warp 1 = tcgen05.mma issuer + TMEM alloc/dealloc |
+//                            warps 2..9 = dequantisers (two groups of 4 on alternating k-blocks), then epilogue |
+//                            warp 10 = activation TMA producer
 // Pipelines (mbarrier):      wfull/wempty[WS]   : TMA  <-> dequant   (int8, 256 k-bytes per stage = 4 MMA k-blocks)
 //                            xfull/xempty[XS]   : TMA  <-> MMA       (activation tile, 64 k)
 //                            a_full/a_empty[4]  : dequant <-> MMA (fp16 A tile)
@@ -50,7 +51,8 @@ constexpr int NUM_A_STAGES = 4;   // fp16 A tiles in flight between the dequant 
 constexpr int DQ_GROUPS    = 2;   // dequant warps work as 2 groups of 4 warps on alternating k-blocks
 constexpr int DQ_WARPS     = 8;
 constexpr int DQ_THREADS   = DQ_WARPS * 32;
-constexpr int TC_THREADS   = 64 + DQ_THREADS;  // warp 0 TMA, warp 1 MMA, 8 dequant/epilogue warps
+constexpr int TC_THREADS   = 64 + DQ_THREADS + 32;  // warp 0 weight TMA, warp 1 MMA, 8 dequant/epilogue warps, warp 10 activation TMA
+constexpr int X_PRODUCER_WARP = 2 + DQ_WARPS;
 constexpr int W8_TILE      = BLOCK_N * BLOCK_K;       // 8192 B of int8
 constexpr int A_TILE       = BLOCK_N * BLOCK_K * 2;   // 16384 B of fp16/bf16
 
@@ -301,18 +303,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (warp == 0) {
         // ============================================================== TMA producer
         if (lane == 0) {
+            // weight stream: free-running (bounded only by its own ring), one 256-k stage per 4 MMA k-blocks
+            for (int wi = 0; wi * W_SUB < num_kb; ++wi) {
+                const int k0       = (kb_begin + wi * W_SUB) * BLOCK_K;
+                const int ws       = wi % WS;
+                const uint32_t wph = (wi / WS) & 1;
+                mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
+                mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
+                // k beyond K is zero-filled by TMA (and never converted: sub-blocks past num_kb are skipped)
+                tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, k0, n_tile * BLOCK_N);
+                tma_load_2d(w8_base + ws * W_STAGE + W_HALF, &map_w, wfull_bar + 8 * ws, k0 + 128, n_tile * BLOCK_N);
+            }
+        }
+    }
+    else if (warp == X_PRODUCER_WARP) {
+        // ============================================================== activation TMA producer (own warp, so a full
+        // activation ring never stalls the weight prefetch)
+        if (lane == 0) {
             for (int it = 0; it < num_kb; ++it) {
-                const int k0 = (kb_begin + it) * BLOCK_K;
-                if ((it % W_SUB) == 0) {
-                    const int wi       = it / W_SUB;
-                    const int ws       = wi % WS;
-                    const uint32_t wph = (wi / WS) & 1;
-                    mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
-                    mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
-                    // k beyond K is zero-filled by TMA (and never converted: sub-blocks past num_kb are skipped)
-                    tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, k0, n_tile * BLOCK_N);
-                    tma_load_2d(w8_base + ws * W_STAGE + W_HALF, &map_w, wfull_bar + 8 * ws, k0 + 128, n_tile * BLOCK_N);
-                }
+                const int k0       = (kb_begin + it) * BLOCK_K;
                 const int xs       = it % XS;
                 const uint32_t xph = (it / XS) & 1;
                 mbar_wait(xempty_bar + 8 * xs, xph ^ 1);
