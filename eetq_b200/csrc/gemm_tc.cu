@@ -56,7 +56,7 @@ constexpr int X_PRODUCER_WARP = 2 + DQ_WARPS;
 constexpr int W8_TILE      = BLOCK_N * BLOCK_K;       // 8192 B of int8
 constexpr int A_TILE       = BLOCK_N * BLOCK_K * 2;   // 16384 B of fp16/bf16
 
-// The int8 weights are staged 256 k-bytes at a time (two 128-byte-wide, 128B-swizzled TMA boxes per stage): the b200
+// The int8 weights are staged 256 k-bytes at a time (one 256-byte-wide TMA box per stage): the b200
 // layout is row-major, so a 64-byte-wide box would touch 128 DRAM pages for 8 KB -- 256 contiguous bytes per row is the
 // widest box TMA allows for 1-byte elements.  Each weight stage therefore feeds 4 consecutive 64-k MMA blocks; the
 // activation tiles keep their own (64-k) stage ring.
@@ -312,7 +312,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
                 // k beyond K is zero-filled by TMA (and never converted: sub-blocks past num_kb are skipped)
                 tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, k0, n_tile * BLOCK_N);
-                tma_load_2d(w8_base + ws * W_STAGE + W_HALF, &map_w, wfull_bar + 8 * ws, k0 + 128, n_tile * BLOCK_N);
             }
         }
     }
@@ -384,16 +383,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int a        = it % NUM_A_STAGES;
             const uint32_t aph = (it / NUM_A_STAGES) & 1;
             mbar_wait(wfull_bar + 8 * ws, wph);       // int8 stage landed
-            // stage = two [128 rows][128 B] halves, 128B-swizzled: 16-byte chunk index ^= (row & 7)
-            const uint8_t* w8 = smem_gen + (w8_base - smem_base) + ws * W_STAGE + (sub_k >> 1) * W_HALF;
+            // stage = [128 rows][256 B] as ONE un-swizzled TMA box: 256-byte rows are the widest TMA allows for 1-byte
+            // elements and halve the number of DRAM requests per stage (the TMA unit, not HBM, bounds a weight stream
+            // made of 128-byte requests); the 2-way LDS bank conflict this costs is negligible next to that
+            const uint8_t* w8 = smem_gen + (w8_base - smem_base) + ws * W_STAGE;
             uint8_t* at       = smem_gen + (a_base - smem_base) + a * A_TILE;
             uint4 in[CHUNKS_PER_THREAD];
 #pragma unroll
             for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
                 const int c   = gt + GROUP_THREADS * j;
                 const int row = c >> 2;
-                const int ci  = (sub_k & 1) * 4 + (c & 3);  // chunk within the 128-byte row of this half
-                in[j] = *reinterpret_cast<const uint4*>(w8 + row * 128 + ((ci ^ (row & 7)) << 4));
+                in[j] = *reinterpret_cast<const uint4*>(w8 + row * 256 + sub_k * 64 + (c & 3) * 16);
             }
             mbar_wait(aempty_bar + 8 * a, aph ^ 1);   // A stage free (the MMA that read it has completed)
 #pragma unroll
@@ -701,8 +701,8 @@ int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scal
         cfg.splits = 1;
     }
     CUtensorMap map_w, map_x;
-    if (int rc = get_tensor_map(w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 100, uint64_t(K), uint64_t(N), uint64_t(K), 128, BLOCK_N,
-                                CU_TENSOR_MAP_SWIZZLE_128B, &map_w))
+    if (int rc = get_tensor_map(w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 100, uint64_t(K), uint64_t(N), uint64_t(K), 256, BLOCK_N,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, &map_w))
         return rc;
     const CUtensorMapDataType xdt = dtype == EETQ_B200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (int rc = get_tensor_map(x, xdt, dtype, uint64_t(K), uint64_t(M), uint64_t(ldx) * 2, BLOCK_K, uint32_t(cfg.bt),
