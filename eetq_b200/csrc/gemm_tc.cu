@@ -14,10 +14,9 @@
 //      B = activation tile          [BT tokens   x 64 k]  fp16/bf16, K-major, 128B-swizzled   (TMA straight from x)
 //      D = fp32 accumulator in TMEM: lane = feature, column = token   (UMMA M = 128, N = BT, K = 16)
 //
-// Warp roles (608 threads):  warps 0..15 = dequantisers (four groups of 4, group g converts k-blocks g mod 4);
-//                            warps 0..7 then run the epilogue | warp 16 = weight TMA producer | warp 17 = tcgen05.mma
-//                            issuer + TMEM alloc/dealloc | warp 18 = activation TMA producer (single-thread roles on the
-//                            highest warp ids: the issue arbiter favours them)
+// Warp roles (352 threads):  warps 0..7 = dequantisers (two groups of 4 on alternating k-blocks), then epilogue |
+//                            warp 8 = weight TMA producer | warp 9 = tcgen05.mma issuer + TMEM alloc/dealloc |
+//                            warp 10 = activation TMA producer   (single-thread roles on the highest warp ids)
 // Pipelines (mbarrier):      wfull/wempty[WS]   : TMA  <-> dequant   (int8, 256 k-bytes per stage = 4 MMA k-blocks)
 //                            xfull/xempty[XS]   : TMA  <-> MMA       (activation tile, 64 k)
 //                            a_full/a_empty[4]  : dequant <-> MMA (fp16 A tile)
@@ -49,17 +48,15 @@ constexpr int BLOCK_N      = 128;  // output features per CTA  (UMMA M)
 constexpr int BLOCK_K      = 64;   // k per pipeline stage (64 fp16 = one 128-byte swizzle row)
 constexpr int UMMA_K       = 16;
 constexpr int NUM_A_STAGES = 4;   // fp16 A tiles in flight between the dequant groups and the MMA issuer
-constexpr int DQ_GROUPS    = 4;   // dequant warps work as 4 groups of 4 warps; group g converts k-blocks it = g (mod 4)
-constexpr int DQ_WARPS     = 16;
-constexpr int EPI_WARPS    = 8;   // warps 0..7 also run the epilogue (two per TMEM lane quadrant)
-constexpr int EPI_THREADS  = EPI_WARPS * 32;
+constexpr int DQ_GROUPS    = 2;   // dequant warps work as 2 groups of 4 warps on alternating k-blocks
+constexpr int DQ_WARPS     = 8;
 constexpr int DQ_THREADS   = DQ_WARPS * 32;
-constexpr int TC_THREADS   = DQ_THREADS + 96;  // 16 dequant warps + weight-TMA, MMA and activation-TMA warps
+constexpr int TC_THREADS   = 64 + DQ_THREADS + 32;  // warp 0 weight TMA, warp 1 MMA, 8 dequant/epilogue warps, warp 10 activation TMA
 // Role -> warp mapping: the single-thread roles get the HIGHEST warp ids (the SM's issue arbiter favours higher warp
 // ids among eligible warps of a sub-partition, so the MMA issuer and the TMA producers are never starved by dequant warps)
-constexpr int W_PRODUCER_WARP = DQ_WARPS;      // 16
-constexpr int MMA_WARP        = DQ_WARPS + 1;  // 17
-constexpr int X_PRODUCER_WARP = DQ_WARPS + 2;  // 18
+constexpr int W_PRODUCER_WARP = DQ_WARPS;      // 8
+constexpr int MMA_WARP        = DQ_WARPS + 1;  // 9
+constexpr int X_PRODUCER_WARP = DQ_WARPS + 2;  // 10
 constexpr int W8_TILE      = BLOCK_N * BLOCK_K;       // 8192 B of int8
 constexpr int A_TILE       = BLOCK_N * BLOCK_K * 2;   // 16384 B of fp16/bf16
 
@@ -284,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tma_prefetch_desc(&map_x);
         for (int s = 0; s < WS; ++s) {
             mbar_init(wfull_bar + 8 * s, 1);
-            mbar_init(wempty_bar + 8 * s, DQ_WARPS);  // every dequant warp reads one 64-k sub-block of each weight stage
+            mbar_init(wempty_bar + 8 * s, DQ_WARPS);  // every dequant warp reads two sub-blocks of each weight stage
         }
         for (int s = 0; s < XS; ++s) {
             mbar_init(xfull_bar + 8 * s, 1);
@@ -420,13 +417,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (lane == 0) {
                 mbar_arrive(afull_bar + 8 * a);
                 // the int8 bytes have been consumed (converted): after this group's last sub-block of the weight stage
-                // hand the stage back to the TMA producer -- once per warp and stage
-                mbar_arrive(wempty_bar + 8 * ws);  // (DQ_GROUPS == W_SUB: this group reads exactly one sub-block per stage)
+                // (sub-blocks 2 / 3, or its final k-block) hand the stage back to the TMA producer -- once per warp
+                if (sub_k >= W_SUB - DQ_GROUPS || it + DQ_GROUPS >= num_kb)
+                    mbar_arrive(wempty_bar + 8 * ws);
             }
         }
 
-        // ---------------------------------------------------------- epilogue (warps 0..7)
-        if (warp < EPI_WARPS) {
+        // ---------------------------------------------------------- epilogue
         mbar_wait(tfull_bar, 0);
         tc_fence_after();
         const int quad   = warp & 3;                 // TMEM lane quadrant this warp may read
@@ -473,7 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     my_part[(c0 + j) * BLOCK_N + quad * 32 + lane] = __uint_as_float(r[j]);
             }
             __threadfence();
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
             // All `splits` CTAs of this tile are co-resident (grid <= 148 CTAs, one per SM): meet at an arrive counter, then
             // EVERY CTA reduces its own 1/splits share of the token columns (in split order -> deterministic) instead of
             // leaving one CTA to walk the whole tile through a chain of dependent L2 round trips.
@@ -485,7 +482,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
                 __threadfence();
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
             const int cs      = BT / p.splits;                 // columns reduced by this CTA (splits is a power of two <= 8)
             const int my_c0   = split * cs;
             const int per_grp = (cs >= 2) ? cs / 2 : cs;       // the two warps of a lane quadrant share the columns
@@ -511,7 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         y[int64_t(t) * p.ldy + n] = from_float<T>(acc * scale_f + bias_f);
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
             if (dt == 0) {
                 // last CTA to leave resets both counters so the workspace stays clean for the next call
                 if (atomicAdd(depart, 1) == p.splits - 1) {
@@ -521,7 +518,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
         }
         tc_fence_before();
-        }
     }
 
     __syncthreads();
