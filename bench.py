@@ -309,8 +309,13 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        # DRAM traffic per launch from the committed `ncu --set full` capture of the four decode GEMV shapes
+        # (profiles/r01_ncu_full_summary.md: dram__bytes_read.sum + dram__bytes_write.sum = 16.83 / 50.41 / 94.16 / 45.17 MB for
+        # o / q|k|v-sized / gate|up / down), averaged per launch like `achieved`; null for other models
+        traffic = (16.834e6 + 50.415e6 + 94.158e6 + 45.173e6) / 4.0 if (s.hidden, s.inter) == (4096, 11008) else None
         roof = {"bound": "hbm", "kernel": "w8a16_gemv_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "us_per_launch": us_per_launch, "bytes_per_launch": bytes_per_launch,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_ncu_full_summary.md (ncu --set full)",
+                "us_per_launch": us_per_launch, "bytes_per_launch": bytes_per_launch,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "how": f"CUDA events around {reps} replays of a graph holding the {n_launch} GEMV launches of one token "
                        "(each on its own layer's weights, 6.5 GB working set)"}
