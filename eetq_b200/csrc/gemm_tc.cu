@@ -14,12 +14,12 @@
 //      B = activation tile          [BT tokens   x 64 k]  fp16/bf16, K-major, 128B-swizzled   (TMA straight from x)
 //      D = fp32 accumulator in TMEM: lane = feature, column = token   (UMMA M = 128, N = BT, K = 16)
 //
-// Warp roles (320 threads):  warps 0..7 = dequantisers: stream int8 weights from global with 128-bit loads (register
-//                            double-buffered, 256 k per super-block), convert, write the fp16 A ring; then epilogue |
-//                            warp 8 = tcgen05.mma issuer + TMEM alloc/dealloc | warp 9 = activation TMA producer
-//                            (single-thread roles on the highest warp ids: the issue arbiter favours them)
-// Pipelines (mbarrier):      xfull/xempty[XS]   : TMA  <-> MMA       (activation tile, 64 k)
-//                            a_full/a_empty[8]  : dequant <-> MMA (fp16 A tile; each dequant group owns 4)
+// Warp roles (352 threads):  warps 0..7 = dequantisers (two groups of 4 on alternating k-blocks), then epilogue |
+//                            warp 8 = weight TMA producer | warp 9 = tcgen05.mma issuer + TMEM alloc/dealloc |
+//                            warp 10 = activation TMA producer   (single-thread roles on the highest warp ids)
+// Pipelines (mbarrier):      wfull/wempty[WS]   : TMA  <-> dequant   (int8, 256 k-bytes per stage = 4 MMA k-blocks)
+//                            xfull/xempty[XS]   : TMA  <-> MMA       (activation tile, 64 k)
+//                            a_full/a_empty[4]  : dequant <-> MMA (fp16 A tile)
 //                            tmem_full          : MMA -> epilogue
 //
 // Arithmetic.  fp16: A = fp16(fp16(q) * s) with ONE rounding per weight and fp32 accumulation -- exactly the
@@ -47,28 +47,33 @@ namespace {
 constexpr int BLOCK_N      = 128;  // output features per CTA  (UMMA M)
 constexpr int BLOCK_K      = 64;   // k per pipeline stage (64 fp16 = one 128-byte swizzle row)
 constexpr int UMMA_K       = 16;
-constexpr int NUM_A_STAGES = 8;   // fp16 A tiles: each dequant group owns 4 (one 256-k super-block = 4 MMA k-blocks)
+constexpr int NUM_A_STAGES = 4;   // fp16 A tiles in flight between the dequant groups and the MMA issuer
 constexpr int DQ_GROUPS    = 2;   // dequant warps work as 2 groups of 4 warps on alternating k-blocks
 constexpr int DQ_WARPS     = 8;
 constexpr int DQ_THREADS   = DQ_WARPS * 32;
-constexpr int TC_THREADS   = DQ_THREADS + 64;  // 8 dequant/epilogue warps + MMA warp + activation-TMA warp
+constexpr int TC_THREADS   = 64 + DQ_THREADS + 32;  // warp 0 weight TMA, warp 1 MMA, 8 dequant/epilogue warps, warp 10 activation TMA
 // Role -> warp mapping: the single-thread roles get the HIGHEST warp ids (the SM's issue arbiter favours higher warp
 // ids among eligible warps of a sub-partition, so the MMA issuer and the TMA producers are never starved by dequant warps)
-constexpr int MMA_WARP        = DQ_WARPS;      // 8
-constexpr int X_PRODUCER_WARP = DQ_WARPS + 1;  // 9
+constexpr int W_PRODUCER_WARP = DQ_WARPS;      // 8
+constexpr int MMA_WARP        = DQ_WARPS + 1;  // 9
+constexpr int X_PRODUCER_WARP = DQ_WARPS + 2;  // 10
 constexpr int W8_TILE      = BLOCK_N * BLOCK_K;       // 8192 B of int8
 constexpr int A_TILE       = BLOCK_N * BLOCK_K * 2;   // 16384 B of fp16/bf16
 
-// The int8 weights never touch shared memory as int8: the dequant warps stream them from global memory with 128-bit
-// loads straight into registers (the TMA unit tops out at ~11 B/clk/SM for data that misses L2 -- measured, DESIGN.md
-// section 5 -- whereas register loads keep >100 KB per SM in flight), 256 k-bytes (= 4 MMA k-blocks, one "super-block") at
-// a time: 16 lanes cover a 256-byte row segment, so DRAM sees 256-byte bursts.  Only the activations use TMA.
-constexpr int W_SUB          = 4;                       // 64-k MMA blocks per super-block
-__host__ __device__ constexpr int x_stages_for(int bt) { return bt >= 256 ? 3 : (bt >= 128 ? 4 : (bt >= 64 ? 6 : 8)); }
+// The int8 weights are staged 256 k-bytes at a time (one 256-byte-wide TMA box per stage): the b200
+// layout is row-major, so a 64-byte-wide box would touch 128 DRAM pages for 8 KB -- 256 contiguous bytes per row is the
+// widest box TMA allows for 1-byte elements.  Each weight stage therefore feeds 4 consecutive 64-k MMA blocks; the
+// activation tiles keep their own (64-k) stage ring.
+constexpr int W_SUB          = 4;                       // 64-k sub-blocks per weight stage
+constexpr int W_STAGE        = W_SUB * W8_TILE;         // 32 KB
+constexpr int W_HALF         = BLOCK_N * 128;           // one 128-byte-wide swizzled box = 16 KB
+__host__ __device__ constexpr int w_stages_for(int bt) { return bt >= 256 ? 2 : (bt >= 64 ? 3 : 4); }
+__host__ __device__ constexpr int x_stages_for(int bt) { return bt >= 256 ? 3 : (bt >= 128 ? 3 : (bt >= 64 ? 4 : 6)); }
 __host__ __device__ constexpr int x_tile_bytes(int bt) { return bt * BLOCK_K * 2; }
 __host__ __device__ constexpr int smem_bytes_for(int bt)
 {
-    return 1024 /*alignment slack*/ + x_stages_for(bt) * x_tile_bytes(bt) + NUM_A_STAGES * A_TILE + 512 /*scales*/ + 512 /*barriers*/;
+    return 1024 /*alignment slack*/ + w_stages_for(bt) * W_STAGE + x_stages_for(bt) * x_tile_bytes(bt) + NUM_A_STAGES * A_TILE
+           + 512 /*barriers*/;
 }
 __host__ __device__ constexpr int tmem_cols_for(int bt) { return bt < 32 ? 32 : bt; }
 
@@ -233,8 +238,9 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------- kernel
 template <typename T, int BT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    w8a16_gemm_tc_kernel(const uint8_t* __restrict__ wq, const __grid_constant__ CUtensorMap map_x, const TcParams p)
+    w8a16_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p)
 {
+    constexpr int WS         = w_stages_for(BT);
     constexpr int XS         = x_stages_for(BT);
     constexpr int X_TILE     = x_tile_bytes(BT);
     constexpr int TMEM_COLS  = tmem_cols_for(BT);
@@ -243,13 +249,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t x_base    = smem_base;                                    // XS x X_TILE
-    const uint32_t a_base    = x_base + XS * X_TILE;                         // 8 x 16 KB
-    const uint32_t sc_base   = a_base + NUM_A_STAGES * A_TILE;               // 128 x half2 (channel scale, duplicated)
-    const uint32_t bar_base  = sc_base + 512;
-    const uint32_t xfull_bar  = bar_base;                 // XS x 8
+    const uint32_t w8_base   = smem_base;                                   // WS x 32 KB (two swizzled 16 KB halves each)
+    const uint32_t x_base    = w8_base + WS * W_STAGE;                       // XS x X_TILE
+    const uint32_t a_base    = x_base + XS * X_TILE;                         // 4 x 16 KB
+    const uint32_t bar_base  = a_base + NUM_A_STAGES * A_TILE;
+    const uint32_t wfull_bar  = bar_base;                 // WS x 8
+    const uint32_t wempty_bar = wfull_bar + WS * 8;       // WS x 8
+    const uint32_t xfull_bar  = wempty_bar + WS * 8;      // XS x 8
     const uint32_t xempty_bar = xfull_bar + XS * 8;       // XS x 8
-    const uint32_t afull_bar  = xempty_bar + XS * 8;      // 8 x 8
+    const uint32_t afull_bar  = xempty_bar + XS * 8;      // 4 x 8
     const uint32_t aempty_bar = afull_bar + NUM_A_STAGES * 8;
     const uint32_t tfull_bar = aempty_bar + NUM_A_STAGES * 8;
     const uint32_t tmem_holder = tfull_bar + 8;
@@ -268,8 +276,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int num_kb   = kb_end - kb_begin;
 
     // ------------------------------------------------------------------ one-time setup
-    if (warp == X_PRODUCER_WARP && lane == 0) {
+    if (warp == W_PRODUCER_WARP && lane == 0) {
+        tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_x);
+        for (int s = 0; s < WS; ++s) {
+            mbar_init(wfull_bar + 8 * s, 1);
+            mbar_init(wempty_bar + 8 * s, DQ_WARPS);  // every dequant warp reads two sub-blocks of each weight stage
+        }
         for (int s = 0; s < XS; ++s) {
             mbar_init(xfull_bar + 8 * s, 1);
             mbar_init(xempty_bar + 8 * s, 1);
@@ -281,17 +294,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_init(tfull_bar, 1);
         fence_barrier_init();
     }
-    if (threadIdx.x < BLOCK_N) {
-        // channel scales of this tile, as duplicated half2 (fp16 path multiplies them into A; zero beyond N)
-        uint32_t v = 0;
-        if constexpr (SCALE_IN_A) {
-            const int n = n_tile * BLOCK_N + int(threadIdx.x);
-            const __half sv  = (n < p.N) ? static_cast<const __half*>(p.scales)[n] : __ushort_as_half(0);
-            const __half2 s2 = __half2half2(sv);
-            v                = *reinterpret_cast<const uint32_t*>(&s2);
-        }
-        *reinterpret_cast<uint32_t*>(smem_gen + (sc_base - smem_base) + threadIdx.x * 4) = v;
-    }
     if (warp == MMA_WARP)
         tmem_alloc(tmem_holder, TMEM_COLS);
     tc_fence_before();
@@ -302,7 +304,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     pdl_launch_dependents();
     pdl_wait_prior_grids();  // x (and y / workspace) may be produced by the previous kernel in the stream
 
-    if (warp == X_PRODUCER_WARP) {
+    if (warp == W_PRODUCER_WARP) {
+        // ============================================================== TMA producer
+        if (lane == 0) {
+            // weight stream: free-running (bounded only by its own ring), one 256-k stage per 4 MMA k-blocks
+            for (int wi = 0; wi * W_SUB < num_kb; ++wi) {
+                const int k0       = (kb_begin + wi * W_SUB) * BLOCK_K;
+                const int ws       = wi % WS;
+                const uint32_t wph = (wi / WS) & 1;
+                mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
+                mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
+                // k beyond K is zero-filled by TMA (and never converted: sub-blocks past num_kb are skipped)
+                tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, k0, n_tile * BLOCK_N);
+            }
+        }
+    }
+    else if (warp == X_PRODUCER_WARP) {
         // ============================================================== activation TMA producer (own warp, so a full
         // activation ring never stalls the weight prefetch)
         if (lane == 0) {
@@ -343,70 +360,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     else {
         // ============================================================== dequantisers, then epilogue
         const int dt = threadIdx.x;       // 0..255 (warps 0..7)
-        // Two groups of 4 warps; group g converts super-blocks sb = g (mod 2) (256 k = 4 MMA k-blocks) into the four A stages
-        // it owns (4g .. 4g+3).  Thread (rowbase = gt / 16, col16 = gt % 16) loads the 16-byte chunk `col16` of rows
-        // rowbase + 8 i (i < 16): 16 lanes cover a 256-byte row segment.  All 16 chunks of a thread belong to MMA k-block
-        // col16 / 4.  The loads of super-block u + 1 are issued BEFORE super-block u is converted (register double buffer).
-        constexpr int GROUP_THREADS = DQ_THREADS / DQ_GROUPS;   // 128
-        constexpr int ROWS_PER_PASS = GROUP_THREADS / 16;       // 8
-        constexpr int PASSES        = BLOCK_N / ROWS_PER_PASS;  // 16
-        const int grp     = dt / GROUP_THREADS;
-        const int gt      = dt % GROUP_THREADS;
-        const int col16   = gt & 15;
-        const int rowbase = gt >> 4;
-        const int sub_k   = col16 >> 2;     // MMA k-block inside the super-block this thread's chunks belong to
-        const int kc      = col16 & 3;      // 16-byte chunk inside that k-block's 64-byte row slice
-        const int num_sb  = (num_kb + W_SUB - 1) / W_SUB;
-        const uint8_t* wrow = wq + (int64_t(n_tile) * BLOCK_N + rowbase) * p.K + int64_t(kb_begin) * BLOCK_K + col16 * 16;
-        const uint32_t* scales_s = reinterpret_cast<const uint32_t*>(smem_gen + (sc_base - smem_base));
-
-        auto load_sb = [&](uint4 (&buf)[PASSES], int sb) {
-            const bool k_ok = (sb * W_SUB + sub_k) < num_kb;
+        // Two groups of 4 warps convert alternating k-blocks, so one group's smem round trips and barrier hops overlap
+        // the other's; inside a group every thread batches its 4 LDS.128 before converting (ILP) and each warp
+        // signals the MMA issuer with ONE elected mbarrier arrive.
+        constexpr int GROUP_THREADS     = DQ_THREADS / DQ_GROUPS;             // 128
+        constexpr int CHUNKS_PER_THREAD = (W8_TILE / 16) / GROUP_THREADS;     // 4
+        const int grp = dt / GROUP_THREADS;
+        const int gt  = dt % GROUP_THREADS;
+        // this thread always converts the same rows: fetch their channel scales once
+        uint32_t scale2[CHUNKS_PER_THREAD];
 #pragma unroll
-            for (int i = 0; i < PASSES; ++i) {
-                const int row = rowbase + ROWS_PER_PASS * i;
-                if (k_ok && n_tile * BLOCK_N + row < p.N)
-                    buf[i] = ldg_stream_128(wrow + int64_t(ROWS_PER_PASS * i) * p.K + int64_t(sb) * (W_SUB * BLOCK_K));
-                else
-                    buf[i] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);  // biased zero
+        for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
+            scale2[j] = 0;
+            if constexpr (SCALE_IN_A) {
+                const int n      = n_tile * BLOCK_N + ((gt + GROUP_THREADS * j) >> 2);
+                const __half sv  = (n < p.N) ? static_cast<const __half*>(p.scales)[n] : __ushort_as_half(0);
+                const __half2 s2 = __half2half2(sv);
+                scale2[j]        = *reinterpret_cast<const uint32_t*>(&s2);
             }
-        };
-        auto convert_sb = [&](uint4 (&buf)[PASSES], int sb, int u) {
-            const int nsub = min(W_SUB, num_kb - sb * W_SUB);   // k-blocks present in this super-block
-            const int a    = grp * W_SUB + sub_k;                // A stage this thread writes
-            if (sub_k < nsub) {
-                mbar_wait(aempty_bar + 8 * a, (u & 1) ^ 1);      // the MMA that read this A stage last has completed
-                uint8_t* at = smem_gen + (a_base - smem_base) + a * A_TILE;
+        }
+        for (int it = grp; it < num_kb; it += DQ_GROUPS) {
+            const int wi       = it / W_SUB;
+            const int sub_k    = it % W_SUB;          // which 64-k slice of the 256-k weight stage
+            const int ws       = wi % WS;
+            const uint32_t wph = (wi / WS) & 1;
+            const int a        = it % NUM_A_STAGES;
+            const uint32_t aph = (it / NUM_A_STAGES) & 1;
+            mbar_wait(wfull_bar + 8 * ws, wph);       // int8 stage landed
+            // stage = [128 rows][256 B] as ONE un-swizzled TMA box: 256-byte rows are the widest TMA allows for 1-byte
+            // elements and halve the number of DRAM requests per stage (the TMA unit, not HBM, bounds a weight stream
+            // made of 128-byte requests); the 2-way LDS bank conflict this costs is negligible next to that
+            const uint8_t* w8 = smem_gen + (w8_base - smem_base) + ws * W_STAGE;
+            uint8_t* at       = smem_gen + (a_base - smem_base) + a * A_TILE;
+            uint4 in[CHUNKS_PER_THREAD];
 #pragma unroll
-                for (int i = 0; i < PASSES; ++i) {
-                    const int row = rowbase + ROWS_PER_PASS * i;
-                    uint4 o0, o1;
-                    dequant16<T>(buf[i], scales_s[row], o0, o1);
-                    uint8_t* rowp = at + row * 128;               // 128B swizzle: 16-byte chunk index XOR (row & 7)
-                    *reinterpret_cast<uint4*>(rowp + (((2 * kc) ^ (row & 7)) << 4))     = o0;
-                    *reinterpret_cast<uint4*>(rowp + (((2 * kc + 1) ^ (row & 7)) << 4)) = o1;
-                }
+            for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
+                const int c   = gt + GROUP_THREADS * j;
+                const int row = c >> 2;
+                in[j] = *reinterpret_cast<const uint4*>(w8 + row * 256 + sub_k * 64 + (c & 3) * 16);
+            }
+            mbar_wait(aempty_bar + 8 * a, aph ^ 1);   // A stage free (the MMA that read it has completed)
+#pragma unroll
+            for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
+                const int c   = gt + GROUP_THREADS * j;  // 16-byte chunk index in the [128][64 B] slice
+                const int row = c >> 2;
+                const int kc  = c & 3;
+                uint4 o0, o1;
+                dequant16<T>(in[j], scale2[j], o0, o1);
+                // 128B swizzle: 16-byte chunk index XOR (row & 7)
+                uint8_t* rowp = at + row * 128;
+                *reinterpret_cast<uint4*>(rowp + (((2 * kc) ^ (row & 7)) << 4))     = o0;
+                *reinterpret_cast<uint4*>(rowp + (((2 * kc + 1) ^ (row & 7)) << 4)) = o1;
             }
             fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) {
-                for (int j = 0; j < nsub; ++j)   // every warp of the group contributed to all four A tiles
-                    mbar_arrive(afull_bar + 8 * (grp * W_SUB + j));
-            }
-        };
-
-        uint4 wbuf[2][PASSES];
-        if (grp < num_sb)
-            load_sb(wbuf[0], grp);
-        int u = 0;
-        for (int sb = grp; sb < num_sb; sb += 2 * DQ_GROUPS, u += 2) {
-            if (sb + DQ_GROUPS < num_sb)
-                load_sb(wbuf[1], sb + DQ_GROUPS);
-            convert_sb(wbuf[0], sb, u);
-            if (sb + DQ_GROUPS < num_sb) {
-                if (sb + 2 * DQ_GROUPS < num_sb)
-                    load_sb(wbuf[0], sb + 2 * DQ_GROUPS);
-                convert_sb(wbuf[1], sb + DQ_GROUPS, u + 1);
+                mbar_arrive(afull_bar + 8 * a);
+                // the int8 bytes have been consumed (converted): after this group's last sub-block of the weight stage
+                // (sub-blocks 2 / 3, or its final k-block) hand the stage back to the TMA producer -- once per warp
+                if (sub_k >= W_SUB - DQ_GROUPS || it + DQ_GROUPS >= num_kb)
+                    mbar_arrive(wempty_bar + 8 * ws);
             }
         }
 
@@ -620,7 +633,7 @@ TcConfig choose_config(int64_t M, int64_t N, int64_t K)
 }
 
 template <typename T, int BT>
-int launch_tc(const uint8_t* wq, const CUtensorMap& map_x, const TcParams& p, const TcConfig& cfg, bool pdl, cudaStream_t stream)
+int launch_tc(const CUtensorMap& map_w, const CUtensorMap& map_x, const TcParams& p, const TcConfig& cfg, bool pdl, cudaStream_t stream)
 {
     auto kernel = w8a16_gemm_tc_kernel<T, BT>;
     constexpr int smem = smem_bytes_for(BT);
@@ -641,7 +654,7 @@ int launch_tc(const uint8_t* wq, const CUtensorMap& map_x, const TcParams& p, co
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs                                           = attr;
     lc.numAttrs                                        = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&lc, kernel, wq, map_x, p);
+    cudaError_t e = cudaLaunchKernelEx(&lc, kernel, map_w, map_x, p);
     count_launch();
     if (e != cudaSuccess) {
         set_error("gemm_tc launch failed: %s", cudaGetErrorString(e));
@@ -651,14 +664,14 @@ int launch_tc(const uint8_t* wq, const CUtensorMap& map_x, const TcParams& p, co
 }
 
 template <typename T>
-int launch_tc_bt(const uint8_t* wq, const CUtensorMap& map_x, const TcParams& p, const TcConfig& cfg, bool pdl, cudaStream_t stream)
+int launch_tc_bt(const CUtensorMap& map_w, const CUtensorMap& map_x, const TcParams& p, const TcConfig& cfg, bool pdl, cudaStream_t stream)
 {
     switch (cfg.bt) {
-        case 16: return launch_tc<T, 16>(wq, map_x, p, cfg, pdl, stream);
-        case 32: return launch_tc<T, 32>(wq, map_x, p, cfg, pdl, stream);
-        case 64: return launch_tc<T, 64>(wq, map_x, p, cfg, pdl, stream);
-        case 128: return launch_tc<T, 128>(wq, map_x, p, cfg, pdl, stream);
-        default: return launch_tc<T, 256>(wq, map_x, p, cfg, pdl, stream);
+        case 16: return launch_tc<T, 16>(map_w, map_x, p, cfg, pdl, stream);
+        case 32: return launch_tc<T, 32>(map_w, map_x, p, cfg, pdl, stream);
+        case 64: return launch_tc<T, 64>(map_w, map_x, p, cfg, pdl, stream);
+        case 128: return launch_tc<T, 128>(map_w, map_x, p, cfg, pdl, stream);
+        default: return launch_tc<T, 256>(map_w, map_x, p, cfg, pdl, stream);
     }
 }
 
@@ -691,7 +704,10 @@ int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scal
         // no (or too small a) workspace: fall back to a single split rather than failing
         cfg.splits = 1;
     }
-    CUtensorMap map_x;
+    CUtensorMap map_w, map_x;
+    if (int rc = get_tensor_map(w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 100, uint64_t(K), uint64_t(N), uint64_t(K), 256, BLOCK_N,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, &map_w))
+        return rc;
     const CUtensorMapDataType xdt = dtype == EETQ_B200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (int rc = get_tensor_map(x, xdt, dtype, uint64_t(K), uint64_t(M), uint64_t(ldx) * 2, BLOCK_K, uint32_t(cfg.bt),
                                 CU_TENSOR_MAP_SWIZZLE_128B, &map_x))
@@ -711,8 +727,8 @@ int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scal
         p.partials      = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + counters_bytes(cfg));
     }
     if (dtype == EETQ_B200_F16)
-        return launch_tc_bt<__half>(reinterpret_cast<const uint8_t*>(w), map_x, p, cfg, pdl, stream);
-    return launch_tc_bt<__nv_bfloat16>(reinterpret_cast<const uint8_t*>(w), map_x, p, cfg, pdl, stream);
+        return launch_tc_bt<__half>(map_w, map_x, p, cfg, pdl, stream);
+    return launch_tc_bt<__nv_bfloat16>(map_w, map_x, p, cfg, pdl, stream);
 }
 
 }  // namespace eetq_b200
