@@ -274,9 +274,7 @@ extern __shared__ float gemv_partial[];
 
 // Kernel selection (development knobs, read once):
 //   EETQ_B200_GEMV_IMPL = ldg (default: register double-buffered LDG kernel) | tma (cp.async.bulk ring kernel)
-//   EETQ_B200_GEMV_CTAS = CTAs per SM the grid is sized for (default 2 for ldg, 1 for tma)
-//   EETQ_B200_GEMV_LOWREG = 1: ldg kernel compiled for 4 CTAs/SM (<= 64 registers) so that, under PDL, the next
-//                              kernel's CTAs co-reside and prefetch while this one streams
+//   EETQ_B200_GEMV_PREFETCH = 1: issue only ONE row group of weight loads before the dependency wait (default 2)
 int gemv_impl()
 {
     static int impl = -1;
@@ -286,29 +284,16 @@ int gemv_impl()
     }
     return impl;
 }
-int gemv_ctas_per_sm(int dflt)
+int gemv_prefetch_groups()
 {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("EETQ_B200_GEMV_CTAS");
-        v             = (e != nullptr) ? atoi(e) : 0;
+        const char* e = getenv("EETQ_B200_GEMV_PREFETCH");
+        v             = (e != nullptr && e[0] == '1') ? 1 : 2;
     }
-    return v > 0 ? v : dflt;
+    return v;
 }
-bool gemv_lowreg()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("EETQ_B200_GEMV_LOWREG");
-        v             = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
-
-constexpr __host__ __device__ int min_ctas(int M, int KITERS, bool XREG, bool LOW = false)
-{
-    return LOW ? (KITERS <= 2 ? 4 : 3) : ((XREG && M * KITERS <= 4) ? 2 : 1);
-}
+constexpr __host__ __device__ int min_ctas(int M, int KITERS, bool XREG) { return (XREG && M * KITERS <= 4) ? 2 : 1; }
 
 // Optional fusions around the GEMV (decode-side glue folded into the hot kernel; all pointers may be null):
 //   xmode GEMV_X_RMSNORM : the activation is RMS-normalised on load (x is the residual stream, norm_weight [K])
@@ -322,6 +307,7 @@ struct GemvFuse {
     float eps;
     int xmode;
     GemvP2P p2p;
+    int prefetch_groups;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long addr, unsigned v)
@@ -371,8 +357,8 @@ __device__ __forceinline__ void p2p_signal_and_wait(const GemvP2P& pp, int tid)
     }
 }
 
-template <typename T, int M, int KITERS, int R, bool XREG, bool LOW = false>
-__global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG, LOW))
+template <typename T, int M, int KITERS, int R, bool XREG>
+__global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
     w8a16_gemv_kernel(const T* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ w, const T* __restrict__ scales,
                       const T* __restrict__ bias, T* __restrict__ y, int64_t ldy, int N, int K, const GemvFuse<T> fuse)
 {
@@ -423,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG, LOW))
         // weights do not depend on the previous kernel: start streaming before the dependency wait
         if (ngroups > 0)
             load_group(wb[0], 0);
-        if (ngroups > 1)
+        if (ngroups > 1 && fuse.prefetch_groups >= 2)
             load_group(wb[1], 1);
         pdl_wait_prior_grids();
 
@@ -441,6 +427,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG, LOW))
                 else
                     xs[m][i].load(x + int64_t(m) * ldx + int64_t(c) * 16);
             }
+        if (ngroups > 1 && fuse.prefetch_groups < 2)
+            load_group(wb[1], 1);  // experiment: activation loads go out ahead of the second weight group
         if (fuse.xmode == GEMV_X_RMSNORM) {
             // every CTA holds the whole activation row across its threads: block-reduce sum(x^2), normalise in registers
 #pragma unroll
@@ -993,7 +981,7 @@ int launch_stream(const T* x, int64_t ldx, const uint8_t* w, const T* scales, co
     }
     auto kernel           = w8a16_gemv_stream_kernel<T, M, KITERS, R>;
     const int stage_bytes = R * K;
-    const int ctas        = gemv_ctas_per_sm(1);
+    const int ctas        = 1;
     int stages            = (kRingBytes / ctas) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
@@ -1034,7 +1022,7 @@ int launch_stream(const T* x, int64_t ldx, const uint8_t* w, const T* scales, co
     return EETQ_B200_OK;
 }
 
-template <typename T, int M, int KITERS, int R, bool XREG, bool LOW = false>
+template <typename T, int M, int KITERS, int R, bool XREG>
 int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N,
                    int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
@@ -1043,9 +1031,9 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
         set_error("gemv: device query failed");
         return EETQ_B200_ECUDA;
     }
-    constexpr int kCtasPerSm = LOW ? 2 : min_ctas(M, KITERS, XREG);
+    constexpr int kCtasPerSm = min_ctas(M, KITERS, XREG);
     constexpr int kMaxRows   = 96;  // rows per CTA bound (sizes the partial-sum buffer)
-    int grid                 = di.sm_count * gemv_ctas_per_sm(kCtasPerSm);
+    int grid                 = di.sm_count * kCtasPerSm;
     // keep rows/CTA <= kMaxRows, and grid a multiple of the SM count
     while ((N + grid - 1) / grid > kMaxRows)
         grid += di.sm_count;
@@ -1067,7 +1055,7 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
     cfg.numAttrs                                       = pdl ? 1 : 0;
 
     const cudaError_t e =
-        cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG, LOW>, x, ldx, w, scales, bias, y, ldy, N, K, fuse);
+        cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG>, x, ldx, w, scales, bias, y, ldy, N, K, fuse);
     count_launch();
     if (e != cudaSuccess) {
         set_error("gemv launch failed: %s", cudaGetErrorString(e));
@@ -1096,13 +1084,6 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
         EB_STREAM_CASE(3, 1)
         EB_STREAM_CASE(4, 1)
 #undef EB_STREAM_CASE
-    }
-    if (gemv_lowreg()) {
-        if constexpr (M == 1 && DTypeOf<T>::value == EETQ_B200_F16) {
-            if (kiters == 1) return launch_variant<T, 1, 1, 4, true, true>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-            if (kiters == 2) return launch_variant<T, 1, 2, 2, true, true>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-            if (kiters == 3) return launch_variant<T, 1, 3, 1, true, true>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        }
     }
 #define EB_GEMV_CASE(KI, RS, RB)                                                                                        \
     if (kiters == KI) {                                                                                                 \
@@ -1204,13 +1185,13 @@ int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales,
     const uint8_t* wu = reinterpret_cast<const uint8_t*>(w);
     if (dtype == EETQ_B200_F16) {
         using T = __half;
-        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p};
+        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p, gemv_prefetch_groups()};
         return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
                              static_cast<T*>(y), ldy, M, int(N), int(K), f, pdl, stream);
     }
     if (dtype == EETQ_B200_BF16) {
         using T = __nv_bfloat16;
-        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p};
+        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p, gemv_prefetch_groups()};
         return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
                              static_cast<T*>(y), ldy, M, int(N), int(K), f, pdl, stream);
     }
