@@ -64,6 +64,9 @@ struct GemvP2P {
     unsigned* ticket                = nullptr;  // local CTA ticket (zero between calls)
     const int* epoch                = nullptr;  // device counter, strictly increasing per decode step
     int world                       = 1;
+    // consumer side: flags of the call that produced THIS kernel's input (all ranks must have published `*epoch` there
+    // before the activation is read); nullptr = the input was produced locally
+    const unsigned* wait_flags      = nullptr;
 };
 struct GemvExtras {
     const void* norm_weight = nullptr;  // [K], GEMV_X_RMSNORM
@@ -130,6 +133,22 @@ __device__ __forceinline__ uint4 ldg_stream_128(const void* p)
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+}
+
+// wait until every rank has published `epoch` in flags[0..world) (written by peers with st.release.sys); all threads of
+// the CTA must call it (contains a __syncthreads)
+__device__ __forceinline__ void p2p_wait_flags(const unsigned* flags, int world, const int* epoch_ptr)
+{
+    if (flags != nullptr) {
+        if (int(threadIdx.x) < world) {
+            const unsigned epoch = unsigned(*epoch_ptr);
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            } while (v < epoch);
+        }
+        __syncthreads();
+    }
 }
 
 // programmatic dependent launch (PDL) controls; no-ops when the kernel was launched without the attribute

@@ -42,11 +42,13 @@ __global__ void __launch_bounds__(256) embed_kernel(const __half* __restrict__ t
 
 // y = fp16( fp16(x_f32 * rsqrt(mean(x^2) + eps)) * w )   (HF LlamaRMSNorm arithmetic), one CTA per row
 __global__ void __launch_bounds__(512) rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
-                                                       __half* __restrict__ y, int H, float eps)
+                                                       __half* __restrict__ y, int H, float eps, const unsigned* wait_flags,
+                                                       int world, const int* epoch)
 {
     __shared__ float red[16];
     pdl_launch_dependents();
     pdl_wait_prior_grids();
+    p2p_wait_flags(wait_flags, world, epoch);
     const __half* xr = x + int64_t(blockIdx.x) * H;
     __half* yr       = y + int64_t(blockIdx.x) * H;
     float ss = 0.f;
@@ -102,7 +104,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
                                                                   const __half* __restrict__ sin_t, const int* __restrict__ pos_p,
                                                                   __half* __restrict__ kcache, __half* __restrict__ vcache,
                                                                   float* __restrict__ partial, int* __restrict__ tickets,
-                                                                  __half* __restrict__ out, int H, int max_ctx, float scale)
+                                                                  __half* __restrict__ out, int H, int max_ctx, float scale,
+                                                                  const unsigned* wait_flags, int world, const int* epoch)
 {
     __shared__ float q_s[ATT_D];
     __shared__ __align__(16) __half knew[ATT_D];
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
         rope_s = __half2float(sin_t[int64_t(pos) * (ATT_D / 2) + t]);
     }
     pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
+    p2p_wait_flags(wait_flags, world, epoch);  // column-sharded q|k|v: every rank's slice must have landed
 
     // RoPE of q (every CTA) and of the new k (owner CTA); HF rotate_half convention evaluated in fp16
     if (t < ATT_D / 2) {
@@ -305,6 +309,12 @@ using namespace eetq_b200;
 
 extern "C" {
 
+int eetq_b200_decode_rmsnorm_p2p(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, const void* wait_flags,
+                                 int world, const void* epoch, int pdl, void* stream);
+int eetq_b200_decode_attention_p2p(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
+                                   void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
+                                   const void* wait_flags, int world, const void* epoch, int pdl, void* stream);
+
 int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, int pdl, void* stream)
 {
     EB_CHECK_ARG(table && token_i64 && x && H % 8 == 0, "decode_embed: bad argument");
@@ -319,12 +329,19 @@ int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, in
 
 int eetq_b200_decode_rmsnorm(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, int pdl, void* stream)
 {
+    return eetq_b200_decode_rmsnorm_p2p(x, w, y, M, H, eps, nullptr, 1, nullptr, pdl, stream);
+}
+
+int eetq_b200_decode_rmsnorm_p2p(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, const void* wait_flags,
+                                 int world, const void* epoch, int pdl, void* stream)
+{
     EB_CHECK_ARG(x && w && y && M > 0 && H > 0, "decode_rmsnorm: bad argument");
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, dim3(unsigned(M)), dim3(512), 0, pdl != 0, static_cast<cudaStream_t>(stream));
     EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rmsnorm_kernel, static_cast<const __half*>(x), static_cast<const __half*>(w),
-                                     static_cast<__half*>(y), int(H), eps));
+                                     static_cast<__half*>(y), int(H), eps, static_cast<const unsigned*>(wait_flags), world,
+                                     static_cast<const int*>(epoch)));
     count_launch();
     return EETQ_B200_OK;
 }
@@ -339,6 +356,14 @@ int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* s
                                void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
                                int pdl, void* stream)
 {
+    return eetq_b200_decode_attention_p2p(qkv, cos_t, sin_t, pos_i32, kcache, vcache, partial, tickets, out, H, D, max_ctx, nullptr, 1,
+                                          nullptr, pdl, stream);
+}
+
+int eetq_b200_decode_attention_p2p(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
+                                   void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
+                                   const void* wait_flags, int world, const void* epoch, int pdl, void* stream)
+{
     EB_CHECK_ARG(qkv && cos_t && sin_t && pos_i32 && kcache && vcache && partial && tickets && out,
                  "decode_attention: null pointer argument");
     EB_CHECK_ARG(D == ATT_D && H % D == 0, "decode_attention: head_dim must be 128");
@@ -351,7 +376,8 @@ int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* s
     EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_fused_kernel, static_cast<const __half*>(qkv), static_cast<const __half*>(cos_t),
                                      static_cast<const __half*>(sin_t), static_cast<const int*>(pos_i32), static_cast<__half*>(kcache),
                                      static_cast<__half*>(vcache), static_cast<float*>(partial), static_cast<int*>(tickets),
-                                     static_cast<__half*>(out), int(H), int(max_ctx), 1.0f / sqrtf(float(D))));
+                                     static_cast<__half*>(out), int(H), int(max_ctx), 1.0f / sqrtf(float(D)),
+                                     static_cast<const unsigned*>(wait_flags), world, static_cast<const int*>(epoch)));
     count_launch();
     return EETQ_B200_OK;
 }
@@ -394,7 +420,7 @@ int eetq_b200_w8a16_gemv_chain(const void* phases, int nphases, void* counters, 
 int eetq_b200_w8a16_gemv_fused_p2p(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
                                    float eps, int xmode, const void* residual, int64_t ldr, int64_t M, int64_t N_local, int64_t K,
                                    int dtype, int world, const uint64_t* peer_y, const uint64_t* peer_flag, const void* local_flags,
-                                   void* ticket, const void* epoch, int64_t ldy, int pdl, void* stream)
+                                   const void* wait_flags, void* ticket, const void* epoch, int64_t ldy, int pdl, void* stream)
 {
     EB_CHECK_ARG(x && w_b200 && scales && peer_y && peer_flag && local_flags && ticket && epoch, "gemv_fused_p2p: null pointer argument");
     EB_CHECK_ARG(world >= 2 && world <= 8, "gemv_fused_p2p: world must be in [2, 8]");
@@ -412,6 +438,7 @@ int eetq_b200_w8a16_gemv_fused_p2p(const void* x, int64_t ldx, const int8_t* w_b
         ex.p2p.peer_flag[r] = peer_flag[r];
     }
     ex.p2p.local_flags = static_cast<const unsigned*>(local_flags);
+    ex.p2p.wait_flags  = static_cast<const unsigned*>(wait_flags);
     ex.p2p.ticket      = static_cast<unsigned*>(ticket);
     ex.p2p.epoch       = static_cast<const int*>(epoch);
     void* y_self       = reinterpret_cast<void*>(peer_y[0]);  // unused in p2p mode (stores go through peer_y)

@@ -335,7 +335,7 @@ __device__ __forceinline__ void store_out(T* y, int64_t idx, T o, const GemvP2P&
     }
 }
 
-// after all stores of this CTA: publish + wait (last CTA only).  Must be called by every thread of the CTA.
+// after all stores of this CTA: the last CTA publishes this rank's flag on every peer.  Called by every thread of the CTA.
 __device__ __forceinline__ void p2p_signal_and_wait(const GemvP2P& pp, int tid)
 {
     if (pp.world <= 1)
@@ -350,9 +350,8 @@ __device__ __forceinline__ void p2p_signal_and_wait(const GemvP2P& pp, int tid)
             const unsigned epoch = unsigned(*pp.epoch);
             for (int r = 0; r < pp.world; ++r)
                 st_release_sys(pp.peer_flag[r], epoch);
-            for (int r = 0; r < pp.world; ++r)
-                while (ld_acquire_sys(pp.local_flags + r) < epoch) {
-                }
+            // no wait here: the CONSUMER of this buffer polls the flags in its prologue (p2p_wait_flags), after it has
+            // issued its own weight prefetch, so the NVLink latency overlaps the next kernel's launch and prefetch
         }
     }
 }
@@ -412,6 +411,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
         if (ngroups > 1 && fuse.prefetch_groups >= 2)
             load_group(wb[1], 1);
         pdl_wait_prior_grids();
+        p2p_wait_flags(fuse.p2p.wait_flags, fuse.p2p.world, fuse.p2p.epoch);  // gathered input: all ranks' slices present?
 
         XSlice<T> xs[M][KITERS];
         float xoff[M];
@@ -498,6 +498,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
     else {
         // ------------------------------------------------------------------ activations re-read through L1 (any M, any K)
         pdl_wait_prior_grids();
+        p2p_wait_flags(fuse.p2p.wait_flags, fuse.p2p.world, fuse.p2p.epoch);
         const int kiters = (nchunks + kThreads - 1) / kThreads;
         for (int g = 0; g < ngroups; ++g) {
             float acc[M][R];

@@ -305,8 +305,16 @@ class W8A16LlamaDecoder:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _gemv(self, x, ldx, lin: _ShardedLinear, y_full, *, norm_w=None, xmode=0, residual_full=None):
-        """y_full[n_begin : n_begin + n_local] = fused GEMV over this rank's rows; then all-gather if sharded."""
+    def _flags_ptr(self, slot):
+        """Address of this rank's flags[slot][0..world) inside the symmetric arena (None -> NULL)."""
+        if slot is None or self._p2p is None:
+            return ctypes.c_void_p(0)
+        p = self._p2p
+        return ctypes.c_void_p(p["arena"].data_ptr() + p["offs"]["flags"] + (slot * 8) * 4)
+
+    def _gemv(self, x, ldx, lin: _ShardedLinear, y_full, *, norm_w=None, xmode=0, residual_full=None, wait_slot=None):
+        """y_full[n_begin : n_begin + n_local] = fused GEMV over this rank's rows; then all-gather if sharded.
+        p2p mode: returns the flag slot this call publishes; `wait_slot` is the slot of the call that produced `x`."""
         off = lin.n_begin
         y = y_full[off:off + lin.n_local]
         res = None if residual_full is None else residual_full[off:off + lin.n_local]
@@ -317,10 +325,10 @@ class W8A16LlamaDecoder:
             peer_y, peer_f, local_flags = self._p2p_args(y_full, lin, slot)
             rc = self._L.eetq_b200_w8a16_gemv_fused_p2p(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), _vp(norm_w), float(self.shape.eps), xmode,
                                                         _vp(res), lin.N, 1, lin.n_local, lin.K, _cabi.F16, self.world, peer_y, peer_f,
-                                                        local_flags, _vp(p["ticket"]), _vp(self.epoch), lin.N, 1 if self.pdl else 0,
-                                                        self._stream())
+                                                        local_flags, self._flags_ptr(wait_slot), _vp(p["ticket"]), _vp(self.epoch), lin.N,
+                                                        1 if self.pdl else 0, self._stream())
             _cabi.check(rc, "eetq_b200_w8a16_gemv_fused_p2p")
-            return
+            return slot
         rc = self._L.eetq_b200_w8a16_gemv_fused(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), None, _vp(norm_w), float(self.shape.eps),
                                                 xmode, _vp(res), lin.N, _vp(y), lin.N, 1, lin.n_local, lin.K, _cabi.F16,
                                                 1 if self.pdl else 0, self._stream())
@@ -340,10 +348,11 @@ class W8A16LlamaDecoder:
             self._p2p["slot"] = 0
             self.epoch.add_(1)   # one epoch per decode step; flags[slot] only ever increase
         _cabi.check(L.eetq_b200_decode_embed(_vp(self.embed), _vp(self.token), _vp(self.x), H, pdl, st()), "decode_embed")
-        def attention(li):
-            _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
-                                                     _vp(self.vcache[li]), _vp(self.partial), _vp(self.tickets), _vp(self.attn), H, D,
-                                                     self.max_ctx, pdl, st()), "decode_attention")
+        def attention(li, wait_slot=None):
+            _cabi.check(L.eetq_b200_decode_attention_p2p(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
+                                                         _vp(self.vcache[li]), _vp(self.partial), _vp(self.tickets), _vp(self.attn), H, D,
+                                                         self.max_ctx, self._flags_ptr(wait_slot), self.world, _vp(self.epoch), pdl, st()),
+                        "decode_attention")
 
         if self.chain:
             nl = len(self.layers)
@@ -367,14 +376,18 @@ class W8A16LlamaDecoder:
                 _cabi.check(L.eetq_b200_w8a16_gemv_chain(ctypes.byref(arr), len(phases), _vp(self.chain_counters[li]), _vp(self.epoch),
                                                           pdl, st()), "eetq_b200_w8a16_gemv_chain")
         else:
+            # p2p mode: each call returns the flag slot it publishes; the kernel that consumes its output waits on that slot
+            s_x = None   # slot of the call that produced self.x (None: produced locally by the embedding gather)
             for li, w in enumerate(self.layers):
-                self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1)
-                attention(li)
+                s_qkv = self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1, wait_slot=s_x)
+                attention(li, wait_slot=s_qkv)
                 # x2 = x + o_proj(attn); x = x2 + down(silu(gate) * up)   (ping-pong so no kernel reads what it writes)
-                self._gemv(self.attn, H, w["o"], self.x2, residual_full=self.x)
-                self._gemv(self.x2, H, w["gu"], self.gu, norm_w=w["ln2"], xmode=1)
-                self._gemv(self.gu, 2 * I, w["down"], self.x, xmode=2, residual_full=self.x2)
-        _cabi.check(L.eetq_b200_decode_rmsnorm(_vp(self.x), _vp(self.norm_w), _vp(self.xn), 1, H, float(s.eps), pdl, st()), "decode_rmsnorm")
+                s_o = self._gemv(self.attn, H, w["o"], self.x2, residual_full=self.x)       # attn is local, x already waited for
+                s_gu = self._gemv(self.x2, H, w["gu"], self.gu, norm_w=w["ln2"], xmode=1, wait_slot=s_o)
+                s_x = self._gemv(self.gu, 2 * I, w["down"], self.x, xmode=2, residual_full=self.x2, wait_slot=s_gu)
+        last_slot = s_x if (self._p2p is not None and not self.chain) else None
+        _cabi.check(L.eetq_b200_decode_rmsnorm_p2p(_vp(self.x), _vp(self.norm_w), _vp(self.xn), 1, H, float(s.eps), self._flags_ptr(last_slot),
+                                                   self.world, _vp(self.epoch), pdl, st()), "decode_rmsnorm")
         torch.matmul(self.xn, self.lm_head_w.t(), out=self.logits)       # fp16 lm_head (library GEMV; not quantised)
         self.token.copy_(torch.argmax(self.logits, dim=-1))               # greedy
         self.pos.add_(1)

@@ -166,15 +166,23 @@ int eetq_b200_w8a16_gemv_chain(const void* phases, int nphases, void* counters, 
 
 /* Column-sharded decode GEMV with the activation all-gather FUSED into the epilogue over NVLink peer memory
  * (one all-gather per sharded linear).  Rank r owns rows [r*N/P, (r+1)*N/P) of the linear; every
- * rank stores its slice straight into all ranks' copies of the output vector (peer-mapped symmetric memory), the last
- * CTA publishes flags[slot][rank] = *epoch on every peer and waits for all peers' flags of the same call, so kernel
- * completion implies the whole vector is present locally.  peer_y[r]: rank r's output buffer offset to this rank's
+ * rank stores its slice straight into all ranks' copies of the output vector (peer-mapped symmetric memory) and the last
+ * CTA publishes flags[slot][rank] = *epoch on every peer (st.release.sys).  The kernel that CONSUMES the vector waits for
+ * all ranks' flags of that slot (`wait_flags`, ld.acquire.sys) in its prologue.  peer_y[r]: rank r's output buffer offset to this rank's
  * first row; peer_flag[r]: address on rank r of flags[slot][this rank]; local_flags: this rank's flags[slot][0..world);
  * ticket: local uint32 (zero between calls); epoch: device int32, strictly increasing per decode step. */
 int eetq_b200_w8a16_gemv_fused_p2p(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
                                    float eps, int xmode, const void* residual, int64_t ldr, int64_t M, int64_t N_local, int64_t K,
                                    int dtype, int world, const uint64_t* peer_y, const uint64_t* peer_flag, const void* local_flags,
-                                   void* ticket, const void* epoch, int64_t ldy, int pdl, void* stream);
+                                   const void* wait_flags, void* ticket, const void* epoch, int64_t ldy, int pdl, void* stream);
+/* Consumers of a gathered buffer poll the flags of the call that produced it (wait_flags = that call's local_flags, or
+ * NULL when the input is local) in their prologue -- after their own weight / KV prefetch -- instead of the producer
+ * waiting at its tail.  Same kernels as eetq_b200_decode_rmsnorm / _attention with that wait added. */
+int eetq_b200_decode_rmsnorm_p2p(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, const void* wait_flags,
+                                 int world, const void* epoch, int pdl, void* stream);
+int eetq_b200_decode_attention_p2p(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
+                                   void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
+                                   const void* wait_flags, int world, const void* epoch, int pdl, void* stream);
 /* x[0:H] = table[*token] */
 int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, int pdl, void* stream);
 /* y = RMSNorm(x) * w over M rows of H */
