@@ -54,6 +54,8 @@ SIGNATURES = {
     "eetq_b200_decode_rmsnorm_p2p": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
     "eetq_b200_decode_attention_p2p": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                                                 _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
+    "eetq_b200_w8a16_gemv_fused_kvprefetch": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp, _c_i64, _c_vp, _c_i64,
+                                                       _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
     "eetq_b200_w8a16_gemv_chain": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_int, _c_vp]),
     "eetq_b200_decode_embed": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "eetq_b200_decode_rmsnorm": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_int, _c_vp]),

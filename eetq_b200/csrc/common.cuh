@@ -75,6 +75,13 @@ struct GemvExtras {
     float eps               = 0.f;
     int xmode               = GEMV_X_PLAIN;
     GemvP2P p2p;
+    // optional L2 prefetch issued by the GEMV CTAs once their own weight stream is fully in flight: the KV cache rows
+    // [0, *pf_pos) of every head (layout [heads][max_ctx][128] fp16) that the NEXT kernel (attention) will read
+    const void* pf_k   = nullptr;
+    const void* pf_v   = nullptr;
+    const int* pf_pos  = nullptr;
+    int pf_heads       = 0;
+    int pf_max_ctx     = 0;
 };
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
                 int M, int64_t N, int64_t K, int dtype, const GemvExtras& ex, bool pdl, cudaStream_t stream);

@@ -403,6 +403,29 @@ int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200,
 }
 
 
+// eetq_b200_w8a16_gemv_fused + an L2 prefetch of the KV cache rows [0, *pos) (layout [heads][max_ctx][128] fp16) that the
+// attention kernel launched right after it will read: issued by the GEMV CTAs once their weight stream is in flight.
+int eetq_b200_w8a16_gemv_fused_kvprefetch(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
+                                          float eps, int xmode, const void* residual, int64_t ldr, void* y, int64_t ldy, int64_t M,
+                                          int64_t N, int64_t K, int dtype, const void* kcache, const void* vcache, const void* pos_i32,
+                                          int64_t heads, int64_t max_ctx, int pdl, void* stream)
+{
+    EB_CHECK_ARG(x && w_b200 && scales && y && kcache && vcache && pos_i32, "w8a16_gemv_fused_kvprefetch: null pointer argument");
+    EB_CHECK_ARG(M >= 1 && M <= EETQ_B200_GEMV_MAX_M && K > 0 && N > 0 && K % 64 == 0 && N % 64 == 0, "w8a16_gemv_fused_kvprefetch: bad shape");
+    GemvExtras ex;
+    ex.norm_weight = norm_weight;
+    ex.residual    = residual;
+    ex.ldr         = ldr;
+    ex.eps         = eps;
+    ex.xmode       = xmode;
+    ex.pf_k        = kcache;
+    ex.pf_v        = vcache;
+    ex.pf_pos      = static_cast<const int*>(pos_i32);
+    ex.pf_heads    = int(heads);
+    ex.pf_max_ctx  = int(max_ctx);
+    return launch_gemv(x, ldx, w_b200, scales, nullptr, y, ldy, int(M), N, K, dtype, ex, pdl != 0, static_cast<cudaStream_t>(stream));
+}
+
 // Up to 4 dependent M=1 fp16 GEMVs in one launch (see w8a16_gemv_chain_kernel).  `phases` is an array of
 // eetq_b200_gemv_phase (layout-identical to eetq_b200::GemvChainPhase); counters: >= nphases-1 uint32, zero on first use,
 // PRIVATE to this chain position (they only ever increase); epoch: device int32 >= 1 that increases by 1 per launch.

@@ -308,7 +308,32 @@ struct GemvFuse {
     int xmode;
     GemvP2P p2p;
     int prefetch_groups;
+    const char* pf_k;
+    const char* pf_v;
+    const int* pf_pos;
+    int pf_heads;
+    int pf_max_ctx;
 };
+
+// L2 prefetch of the KV rows the following attention kernel will stream (128-byte lines, spread over the whole grid)
+template <typename T>
+__device__ __forceinline__ void prefetch_kv_l2(const GemvFuse<T>& f)
+{
+    if (f.pf_k == nullptr)
+        return;
+    const int pos            = *f.pf_pos;
+    const int lines_per_head = pos * 2;  // 256 bytes per cached position
+    const int total          = 2 * f.pf_heads * lines_per_head;
+    const int64_t head_bytes = int64_t(f.pf_max_ctx) * 256;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tensor = i / (f.pf_heads * lines_per_head);
+        const int rem    = i - tensor * (f.pf_heads * lines_per_head);
+        const int head   = rem / lines_per_head;
+        const int line   = rem - head * lines_per_head;
+        const char* addr = (tensor ? f.pf_v : f.pf_k) + head * head_bytes + int64_t(line) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+    }
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long addr, unsigned v)
 {
@@ -467,6 +492,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
                 so += xs[m][i].sum;
             xoff[m] = -XSlice<T>::kOffset * so;
         }
+
+        prefetch_kv_l2<T>(fuse);  // hints only: no registers, no waiting
 
         auto compute_group = [&](uint4 (&buf)[R][KITERS], int g) {
             float acc[M][R];
@@ -1186,13 +1213,13 @@ int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales,
     const uint8_t* wu = reinterpret_cast<const uint8_t*>(w);
     if (dtype == EETQ_B200_F16) {
         using T = __half;
-        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p, gemv_prefetch_groups()};
+        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p, gemv_prefetch_groups(), static_cast<const char*>(ex.pf_k), static_cast<const char*>(ex.pf_v), ex.pf_pos, ex.pf_heads, ex.pf_max_ctx};
         return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
                              static_cast<T*>(y), ldy, M, int(N), int(K), f, pdl, stream);
     }
     if (dtype == EETQ_B200_BF16) {
         using T = __nv_bfloat16;
-        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p, gemv_prefetch_groups()};
+        GemvFuse<T> f{static_cast<const T*>(ex.norm_weight), static_cast<const T*>(ex.residual), ex.ldr, ex.eps, ex.xmode, ex.p2p, gemv_prefetch_groups(), static_cast<const char*>(ex.pf_k), static_cast<const char*>(ex.pf_v), ex.pf_pos, ex.pf_heads, ex.pf_max_ctx};
         return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
                              static_cast<T*>(y), ldy, M, int(N), int(K), f, pdl, stream);
     }

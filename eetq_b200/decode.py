@@ -246,6 +246,8 @@ class W8A16LlamaDecoder:
             chain = os.environ.get("EETQ_B200_CHAIN", "0") == "1"   # measured slower than PDL-chained launches
         self.chain = bool(chain) and world_size == 1
         self.chain_counters = torch.zeros(L, 4, dtype=torch.int32, device=dev)
+        # the q|k|v GEMV of a layer prefetches that layer's KV cache rows into L2 for the attention kernel that follows
+        self.kv_prefetch = os.environ.get("EETQ_B200_KV_PREFETCH", "1") != "0"
         self.xn = torch.zeros(1, H, dtype=dt, device=dev)
         self.logits = torch.zeros(1, shape.vocab, dtype=dt, device=dev)
         self._L = _cabi.lib()
@@ -312,7 +314,7 @@ class W8A16LlamaDecoder:
         p = self._p2p
         return ctypes.c_void_p(p["arena"].data_ptr() + p["offs"]["flags"] + (slot * 8) * 4)
 
-    def _gemv(self, x, ldx, lin: _ShardedLinear, y_full, *, norm_w=None, xmode=0, residual_full=None, wait_slot=None):
+    def _gemv(self, x, ldx, lin: _ShardedLinear, y_full, *, norm_w=None, xmode=0, residual_full=None, wait_slot=None, kv_layer=None):
         """y_full[n_begin : n_begin + n_local] = fused GEMV over this rank's rows; then all-gather if sharded.
         p2p mode: returns the flag slot this call publishes; `wait_slot` is the slot of the call that produced `x`."""
         off = lin.n_begin
@@ -329,6 +331,13 @@ class W8A16LlamaDecoder:
                                                         1 if self.pdl else 0, self._stream())
             _cabi.check(rc, "eetq_b200_w8a16_gemv_fused_p2p")
             return slot
+        if kv_layer is not None and self.kv_prefetch and self.world == 1:
+            rc = self._L.eetq_b200_w8a16_gemv_fused_kvprefetch(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), _vp(norm_w), float(self.shape.eps),
+                                                               xmode, _vp(res), lin.N, _vp(y), lin.N, 1, lin.n_local, lin.K, _cabi.F16,
+                                                               _vp(self.kcache[kv_layer]), _vp(self.vcache[kv_layer]), _vp(self.pos),
+                                                               self.shape.heads, self.max_ctx, 1 if self.pdl else 0, self._stream())
+            _cabi.check(rc, "eetq_b200_w8a16_gemv_fused_kvprefetch")
+            return None
         rc = self._L.eetq_b200_w8a16_gemv_fused(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), None, _vp(norm_w), float(self.shape.eps),
                                                 xmode, _vp(res), lin.N, _vp(y), lin.N, 1, lin.n_local, lin.K, _cabi.F16,
                                                 1 if self.pdl else 0, self._stream())
@@ -379,7 +388,7 @@ class W8A16LlamaDecoder:
             # p2p mode: each call returns the flag slot it publishes; the kernel that consumes its output waits on that slot
             s_x = None   # slot of the call that produced self.x (None: produced locally by the embedding gather)
             for li, w in enumerate(self.layers):
-                s_qkv = self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1, wait_slot=s_x)
+                s_qkv = self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1, wait_slot=s_x, kv_layer=li)
                 attention(li, wait_slot=s_qkv)
                 # x2 = x + o_proj(attn); x = x2 + down(silu(gate) * up)   (ping-pong so no kernel reads what it writes)
                 s_o = self._gemv(self.attn, H, w["o"], self.x2, residual_full=self.x)       # attn is local, x already waited for

@@ -146,6 +146,13 @@ int eetq_b200_w8a16_gemm_host(const void* x_host, void* x_dev, const int8_t* w_b
 int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
                                const void* norm_weight, float eps, int xmode, const void* residual, int64_t ldr, void* y,
                                int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, int pdl, void* stream);
+/* eetq_b200_w8a16_gemv_fused that also issues an L2 prefetch of the KV-cache rows [0, *pos) ([heads][max_ctx][128] fp16)
+ * the attention kernel launched right after it will read (the GEMV's own weight stream is already in flight). */
+int eetq_b200_w8a16_gemv_fused_kvprefetch(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
+                                          float eps, int xmode, const void* residual, int64_t ldr, void* y, int64_t ldy, int64_t M,
+                                          int64_t N, int64_t K, int dtype, const void* kcache, const void* vcache, const void* pos_i32,
+                                          int64_t heads, int64_t max_ctx, int pdl, void* stream);
+
 /* Up to 4 DEPENDENT decode GEMVs (M = 1, fp16; e.g. o_proj -> gate|up -> down -> next layer's q|k|v) in ONE launch:
  * the CTAs meet at a grid barrier between phases but issue the next phase's first weight loads before waiting, so the
  * HBM stream does not stop at what would otherwise be kernel boundaries.  counters: nphases-1 uint32 private to this call
