@@ -247,7 +247,8 @@ class W8A16LlamaDecoder:
         self.chain = bool(chain) and world_size == 1
         self.chain_counters = torch.zeros(L, 4, dtype=torch.int32, device=dev)
         # the q|k|v GEMV of a layer prefetches that layer's KV cache rows into L2 for the attention kernel that follows
-        self.kv_prefetch = os.environ.get("EETQ_B200_KV_PREFETCH", "1") != "0"
+        # (measured slower, 551 vs 563 tok/s: off by default)
+        self.kv_prefetch = os.environ.get("EETQ_B200_KV_PREFETCH", "0") == "1"
         self.xn = torch.zeros(1, H, dtype=dt, device=dev)
         self.logits = torch.zeros(1, shape.vocab, dtype=dt, device=dev)
         self._L = _cabi.lib()
