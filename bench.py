@@ -189,6 +189,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     s = shape_of(args)
     ctx_max = args.prompt + args.steps + args.warmup + 64
