@@ -23,8 +23,12 @@
 //   * per-row partial sums are reduced with a transposing warp butterfly (9 shuffles per 8 rows instead of
 //     40) and one shared-memory pass at the end of the CTA;
 //   * the grid is a multiple of the SM count and rows are split evenly (+-1) over CTAs;
-//   * weight loads for the first row group are issued BEFORE griddepcontrol.wait, so under programmatic
-//     dependent launch the HBM stream of layer i+1 starts while layer i drains.
+//   * the weight loads of the first TWO row groups (16 x 16 bytes per thread, ~19 MB chip-wide) are issued BEFORE
+//     griddepcontrol.wait, so under programmatic dependent launch the HBM stream of kernel i+1 starts while
+//     kernel i drains.
+//
+// Also in this file, both opt-in and measured slower than the kernel above: the TMA-bulk shared-
+// memory-ring variant (w8a16_gemv_stream_kernel) and the chained multi-GEMV launch (w8a16_gemv_chain_kernel).
 //
 // Algorithmic bytes per call: K*N + 2*N + 2*M*K + 2*M*N; each weight byte is read exactly once.
 #include <cstdlib>

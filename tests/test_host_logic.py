@@ -87,3 +87,46 @@ def test_argument_validation_before_any_launch():
         eetq_b200.quant_weights(torch.zeros(64, 64, dtype=torch.float16), torch.int32, False)
     with pytest.raises(NotImplementedError):
         eetq_b200.preprocess_weights(w, is_int4=True)
+
+
+def test_eet_quantize_int8_ingest_uses_scb_scales(monkeypatch):
+    """bitsandbytes ingest (quantizer.py:46-48 in the reference): int8 weight + SCB -> scales = SCB / 127, weights only
+    re-laid-out (no re-quantisation).  The native calls are stubbed: this checks the host logic on CPU."""
+    import eetq_b200.modules.qlinear as ql
+
+    calls = {}
+
+    def fake_preprocess(w):
+        calls["pre"] = w.clone()
+        return w
+
+    monkeypatch.setattr(ql, "preprocess_weights", fake_preprocess)
+
+    class FakeBnbLinear(nn.Linear):
+        pass
+
+    lin = FakeBnbLinear(64, 128, bias=False)
+    lin.weight = nn.Parameter(torch.randint(-127, 128, (128, 64), dtype=torch.int8), requires_grad=False)
+    lin.register_buffer("SCB", torch.rand(128) + 0.5)
+
+    class Holder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.proj = lin
+
+    m = Holder()
+    eetq_b200.eet_quantize(m, include=(FakeBnbLinear,))
+    q = m.proj
+    assert isinstance(q, W8A16Linear)
+    assert torch.equal(calls["pre"], lin.weight.t().contiguous())          # [K, N] handed to the layout pass
+    assert torch.allclose(q.weight_scales.float(), (lin.SCB / 127.0).half().float())
+    assert q.qweight.dtype == torch.int8 and q.qweight.shape == (64, 128)
+
+
+def test_quantize_and_preprocess_rejects_unknown_dtype():
+    from eetq_b200.modules.qlinear import quantize_and_preprocess_weights
+
+    with pytest.raises(ValueError, match="Unsupported data type"):
+        quantize_and_preprocess_weights(torch.zeros(64, 64, dtype=torch.int32))
+    with pytest.raises(AssertionError):
+        quantize_and_preprocess_weights(torch.zeros(64, 64, dtype=torch.int8), None)
