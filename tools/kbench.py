@@ -54,12 +54,13 @@ def main():
     ap.add_argument("--out", default="gpurun_out/kbench.json")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--tc-only", action="store_true")
+    ap.add_argument("--gemv-only", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     lib = _cabi.lib()
     results = []
-    shapes = [(4096, 4096), (4096, 11008), (11008, 4096)] if args.tc_only else [(4096, 4096), (4096, 12288), (4096, 22016), (11008, 4096)]
+    shapes = [(4096, 4096), (4096, 11008), (11008, 4096)] if args.tc_only else [(4096, 4096), (4096, 11008), (11008, 4096), (4096, 12288), (4096, 22016)]
 
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_gemv.so")
     ref = ctypes.CDLL(ref_path) if os.path.exists(ref_path) else None
@@ -99,7 +100,7 @@ def main():
             print(json.dumps(r), flush=True)
             results.append(r)
             del wf
-        for M in ([8, 16, 64, 256, 1024] if not args.quick else [16, 1024]):
+        for M in ([] if args.gemv_only else [8, 16, 64, 256, 1024] if not args.quick else [16, 1024]):
             x = torch.randn(M, K, device=dev).half()
             fns = [(lambda w=w: w8_a16_gemm_bias(x, w, sc, None, flags=_cabi.FLAG_FORCE_TC)) for w in ws]
             med, best = time_graph(fns)
