@@ -130,3 +130,14 @@ def test_quantize_and_preprocess_rejects_unknown_dtype():
         quantize_and_preprocess_weights(torch.zeros(64, 64, dtype=torch.int32))
     with pytest.raises(AssertionError):
         quantize_and_preprocess_weights(torch.zeros(64, 64, dtype=torch.int8), None)
+
+
+def test_reference_package_names_resolve():
+    """`import eetq` / `from eetq.modules import W8A16Linear` / `from EETQ import w8_a16_gemm` -- the import lines the
+    reference's own code and examples use (python/eetq/modules/qlinear.py:11, examples/layers/test_qlinear.py)."""
+    import eetq
+    from eetq.modules import W8A16Linear as A
+    from eetq.utils import eet_quantize as q
+    from EETQ import preprocess_weights, quant_weights, w8_a16_gemm  # noqa: F401
+
+    assert A is eetq_b200.W8A16Linear and q is eetq_b200.eet_quantize and eetq.EetqLinear is eetq_b200.EetqLinear
