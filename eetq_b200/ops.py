@@ -54,6 +54,7 @@ def _default_device() -> torch.device:
 # workspace for the split-K tcgen05 path: one zero-initialised buffer per (device, stream), grown on demand
 # ---------------------------------------------------------------------------------------------------------------
 _workspaces = {}
+_retired_workspaces = []  # outgrown buffers stay alive: a captured CUDA graph may still hold their address
 
 
 def _workspace(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
@@ -62,7 +63,9 @@ def _workspace(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
+        if ws is not None:
+            _retired_workspaces.append(ws)
+        ws = torch.zeros(max(2 * nbytes, 1 << 24), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 
