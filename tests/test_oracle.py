@@ -113,3 +113,42 @@ def test_identity_gemm_known_answer(oracle):
     q, s, _ = oracle.quantize(w)
     y = oracle.gemm(torch.eye(64, dtype=torch.float16), q, s)
     assert torch.equal(y, oracle.dequantize(q, s))
+
+
+def test_layout_roundtrips_property(oracle):
+    """Size-independent properties: both layouts are bijections on the K*N bytes; the reference layout only moves and
+    biases bytes (multiset of values preserved); column blocks of the b200 layout are contiguous byte ranges."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(kt=st.integers(1, 4), nt=st.integers(1, 4), seed=st.integers(0, 2**16))
+    def prop(kt, nt, seed):
+        K, N = 64 * kt, 64 * nt
+        g = torch.Generator().manual_seed(seed)
+        q = torch.randint(-128, 128, (K, N), generator=g, dtype=torch.int8)
+        r = oracle.ref_layout(q)
+        assert torch.equal(oracle.ref_layout_inv(r), q)
+        assert torch.equal(torch.sort(r.view(torch.uint8).flatten().to(torch.int16) - 128).values,
+                           torch.sort(q.flatten().to(torch.int16)).values)
+        b = oracle.b200_layout(q)
+        assert torch.equal(oracle.b200_layout_inv(b), q)
+        n0 = 64 * (seed % nt)
+        shard = oracle.b200_layout(q[:, n0:n0 + 64].contiguous())
+        assert torch.equal(b.flatten()[n0 * K:(n0 + 64) * K], shard.flatten())
+
+    prop()
+
+
+def test_quantizer_properties(oracle):
+    """Per-column independence and scale equivariance of the reference quantiser: scaling a column by a power of two
+    scales its scale and leaves q unchanged; permuting rows permutes q."""
+    w = oracle.synth_weight(128, 64, seed=21, dtype=torch.float32)
+    q, s, _ = oracle.quantize(w)
+    w2 = w.clone()
+    w2[:, 7] *= 4.0
+    q2, s2, _ = oracle.quantize(w2)
+    assert torch.equal(q2, q) and torch.equal(s2[7], s[7] * 4) and torch.equal(s2[:7], s[:7])
+    perm = torch.randperm(128, generator=torch.Generator().manual_seed(0))
+    qp, sp, _ = oracle.quantize(w[perm])
+    assert torch.equal(qp, q[perm]) and torch.equal(sp, s)
+    assert int(q.abs().max()) >= 127          # every column uses the full int8 range by construction
