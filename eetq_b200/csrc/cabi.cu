@@ -7,6 +7,7 @@
 // reference lacks; error codes + thread-local message instead of C++ exceptions/asserts;
 // per-device attributes cached once instead of re-queried per forward (fpA_intB_gemm_template.h:390-397).
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -152,24 +153,52 @@ size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K)
 {
     if (M <= 0 || N <= 0 || K <= 0)
         return 0;
-    return gemm_tc_workspace_bytes(M, N, K);
+    size_t need = gemm_tc_workspace_bytes(M, N, K);
+#ifdef EETQ_B200_WITH_V1
+    const size_t v1 = gemm_tc_v1_workspace_bytes(M, N, K);
+    if (v1 > need) need = v1;
+#endif
+    return need;
 }
 
-int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
-                            void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
-                            size_t workspace_bytes, int flags, void* stream)
+namespace {
+// shared argument validation of every w8a16 forward entry point
+int check_forward_args(const char* who, const void* x, int64_t ldx, const void* w, const void* scales, const void* y, int64_t ldy,
+                       int64_t M, int64_t N, int64_t K, int dtype)
 {
-    EB_CHECK_ARG(x && w_b200 && scales && y, "w8a16_gemm: null pointer argument");
-    EB_CHECK_ARG(dtype == EETQ_B200_F16 || dtype == EETQ_B200_BF16, "w8a16_gemm: dtype must be F16 or BF16 (got %d)",
-                 dtype);
-    EB_CHECK_ARG(M >= 0 && M <= (int64_t(1) << 24), "w8a16_gemm: bad M=%lld", (long long)M);
-    if (int rc = check_kn("w8a16_gemm", K, N))
+    EB_CHECK_ARG(x && w && scales && y, "%s: null pointer argument", who);
+    EB_CHECK_ARG(dtype == EETQ_B200_F16 || dtype == EETQ_B200_BF16, "%s: dtype must be F16 or BF16 (got %d)", who, dtype);
+    EB_CHECK_ARG(M >= 0 && M <= (int64_t(1) << 24), "%s: bad M=%lld", who, (long long)M);
+    if (int rc = check_kn(who, K, N))
         return rc;
-    EB_CHECK_ARG(ldx >= K && ldy >= N, "w8a16_gemm: ldx (%lld) < K or ldy (%lld) < N", (long long)ldx, (long long)ldy);
-    EB_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0, "w8a16_gemm: ldx and ldy must be multiples of 8 elements");
-    EB_CHECK_ARG(aligned16(x) && aligned16(w_b200) && aligned16(y), "w8a16_gemm: x, w and y must be 16-byte aligned");
+    EB_CHECK_ARG(ldx >= K && ldy >= N, "%s: ldx (%lld) < K or ldy (%lld) < N", who, (long long)ldx, (long long)ldy);
+    EB_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0, "%s: ldx and ldy must be multiples of 8 elements", who);
+    EB_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y), "%s: x, w and y must be 16-byte aligned", who);
+    return EETQ_B200_OK;
+}
+
+bool use_v1()
+{
+#ifdef EETQ_B200_WITH_V1
+    static const bool v = [] {
+        const char* e = getenv("EETQ_B200_TC_IMPL");
+        return e != nullptr && e[0] == 'v' && e[1] == '1';
+    }();
+    return v;
+#else
+    return false;
+#endif
+}
+
+int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias, const void* residual,
+                  int64_t ldr, void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
+                  size_t workspace_bytes, int flags, unsigned long long* trace, void* stream)
+{
+    if (int rc = check_forward_args("w8a16_gemm", x, ldx, w_b200, scales, y, ldy, M, N, K, dtype))
+        return rc;
     EB_CHECK_ARG(!((flags & EETQ_B200_FLAG_FORCE_GEMV) && (flags & EETQ_B200_FLAG_FORCE_TC)),
                  "w8a16_gemm: FORCE_GEMV and FORCE_TC are exclusive");
+    EB_CHECK_ARG(residual == nullptr || (ldr >= N && (ldr % 8) == 0 && aligned16(residual)), "w8a16_gemm: bad residual stride/alignment");
     if (M == 0)
         return EETQ_B200_OK;  // empty batch: nothing to enqueue
     if (int rc = check_arch())
@@ -181,13 +210,57 @@ int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, co
         EB_CHECK_ARG(M <= EETQ_B200_GEMV_MAX_M, "w8a16_gemm: FORCE_GEMV needs M <= %d", EETQ_B200_GEMV_MAX_M);
         use_gemv = true;
     }
-    if (flags & EETQ_B200_FLAG_FORCE_TC)
+    if ((flags & EETQ_B200_FLAG_FORCE_TC) || trace != nullptr)
         use_gemv = false;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (use_gemv)
-        return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, GemvExtras{}, pdl, s);
-    return launch_gemm_tc(x, ldx, w_b200, scales, bias, y, ldy, M, N, K, dtype, workspace, workspace_bytes, pdl, s);
+    if (use_gemv) {
+        GemvExtras ex;
+        ex.residual = residual;
+        ex.ldr      = ldr;
+        return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl, s);
+    }
+#ifdef EETQ_B200_WITH_V1
+    if (use_v1() && residual == nullptr && trace == nullptr)
+        return launch_gemm_tc_v1(x, ldx, w_b200, scales, bias, y, ldy, M, N, K, dtype, workspace, workspace_bytes, pdl, s);
+#endif
+    return launch_gemm_tc(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, M, N, K, dtype, workspace, workspace_bytes, pdl, trace, s);
+}
+}  // namespace
+
+int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
+                            void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
+                            size_t workspace_bytes, int flags, void* stream)
+{
+    return gemm_dispatch(x, ldx, w_b200, scales, bias, nullptr, 0, y, ldy, M, N, K, dtype, workspace, workspace_bytes, flags, nullptr,
+                         stream);
+}
+
+int eetq_b200_w8a16_gemm_residual(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
+                                  const void* residual, int64_t ldr, void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype,
+                                  void* workspace, size_t workspace_bytes, int flags, void* stream)
+{
+    return gemm_dispatch(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, M, N, K, dtype, workspace, workspace_bytes, flags, nullptr,
+                         stream);
+}
+
+int eetq_b200_w8a16_gemm_trace(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, void* y, int64_t ldy, int64_t M,
+                               int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* trace, size_t trace_bytes,
+                               void* stream)
+{
+    EB_CHECK_ARG(trace != nullptr, "w8a16_gemm_trace: null trace buffer");
+    const size_t need = size_t(gemm_tc_grid_for(M, N, K)) * gemm_tc_trace_slots() * sizeof(unsigned long long);
+    EB_CHECK_ARG(trace_bytes >= need, "w8a16_gemm_trace: trace buffer too small (%zu < %zu)", trace_bytes, need);
+    return gemm_dispatch(x, ldx, w_b200, scales, nullptr, nullptr, 0, y, ldy, M, N, K, EETQ_B200_F16, workspace, workspace_bytes,
+                         EETQ_B200_FLAG_FORCE_TC, static_cast<unsigned long long*>(trace), stream);
+}
+
+int eetq_b200_w8a16_gemm_trace_info(int64_t M, int64_t N, int64_t K, int* grid, int* slots)
+{
+    EB_CHECK_ARG(grid && slots && M > 0 && N > 0 && K > 0, "w8a16_gemm_trace_info: bad argument");
+    *grid  = gemm_tc_grid_for(M, N, K);
+    *slots = gemm_tc_trace_slots();
+    return EETQ_B200_OK;
 }
 
 int eetq_b200_w8a16_gemm(const void* x, const int8_t* w_b200, const void* scales, const void* bias, void* y, int64_t M,
@@ -202,7 +275,8 @@ int eetq_b200_w8a16_gemm_host(const void* x_host, void* x_dev, const int8_t* w_b
                               void* workspace, size_t workspace_bytes, void* stream)
 {
     EB_CHECK_ARG(x_host && x_dev && y_dev && y_host, "w8a16_gemm_host: null pointer argument");
-    EB_CHECK_ARG(M >= 0 && N > 0 && K > 0, "w8a16_gemm_host: bad shape");
+    if (int rc = check_forward_args("w8a16_gemm_host", x_dev, K, w_b200, scales, y_dev, N, M, N, K, dtype))
+        return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (M == 0)
         return EETQ_B200_OK;

@@ -7,34 +7,41 @@
 // (mma.sync + cp.async + ldmatrix, compiled out for sm >= 90) with a Blackwell-native kernel; nothing of the
 // CUTLASS 2.x structure is kept.
 //
-// Formulation (operands swapped so that small token counts stay efficient and the per-channel scale is per
-// accumulator ROW):      D[n, t] = sum_k  A[n, k] * B[t, k]
-//      A = dequantised weight tile  [128 features x 64 k]  fp16/bf16, K-major, 128B-swizzled   (written by the
-//          dequant warps from the int8 tile that TMA staged -- b200 layout rows are already K-major)
-//      B = activation tile          [BT tokens   x 64 k]  fp16/bf16, K-major, 128B-swizzled   (TMA straight from x)
+// Formulation (operands swapped so that small token counts stay efficient and the per-channel scale is a property of
+// an accumulator ROW):      D[n, t] = sum_k  A[n, k] * B[t, k]
+//      A = dequantised weights [128 features x 256 k] fp16/bf16 **in tensor memory** (tcgen05.st by the dequant warps;
+//          the MMA reads its A operand straight from TMEM -- no shared-memory round trip, no async-proxy fence)
+//      B = activation tile     [BT tokens x 64 k]  K-major, 128B-swizzled shared memory   (TMA straight from x)
 //      D = fp32 accumulator in TMEM: lane = feature, column = token   (UMMA M = 128, N = BT, K = 16)
 //
-// Warp roles (352 threads):  warps 0..7 = dequantisers (two groups of 4 on alternating k-blocks), then epilogue |
-//                            warp 8 = weight TMA producer | warp 9 = tcgen05.mma issuer + TMEM alloc/dealloc |
-//                            warp 10 = activation TMA producer   (single-thread roles on the highest warp ids)
-// Pipelines (mbarrier):      wfull/wempty[WS]   : TMA  <-> dequant   (int8, 256 k-bytes per stage = 4 MMA k-blocks)
-//                            xfull/xempty[XS]   : TMA  <-> MMA       (activation tile, 64 k)
-//                            a_full/a_empty[4]  : dequant <-> MMA (fp16 A tile)
-//                            tmem_full          : MMA -> epilogue
+// Persistent stream-K schedule.  The work is cut into UNITS of (128-feature tile, 256-k stage).  The grid is one CTA per SM
+// (never more CTAs than can be resident); CTA g walks the contiguous unit range [g*U/G, (g+1)*U/G), i.e. the tail of one
+// tile, whole tiles, and the head of another.  A tile that is shared by several CTAs is finished by its OWNER (the CTA that
+// holds the tile's first stage -- for which the tile is the LAST segment of its range); the other contributors meet
+// the tile as the FIRST segment of their range, dump their fp32 partial to a workspace slot and raise a flag, long before
+// the owner gets there.  The owner adds the partials in k order (deterministic) and writes y.  A CTA therefore only ever
+// waits for first-segment partials of higher-indexed CTAs, which those produce without waiting for anybody: progress
+// needs no grid-wide co-residency (this replaces round 1's spin-wait split-K; the reference disables split-K altogether by
+// passing a null workspace, fpA_intB_gemm_wrapper.cu:169-170).
+//
+// Warp roles ((7 + DQW) warps):  warps 0..3   epilogue (TMEM -> registers -> y / workspace), one per TMEM lane quadrant
+//                                warps 4..4+DQW-1  dequantisers: int8 smem -> fp16/bf16 registers -> TMEM (tcgen05.st)
+//                                warp 4+DQW   weight TMA producer | 5+DQW  tcgen05.mma issuer + TMEM alloc | 6+DQW  activation TMA
+//                                (single-thread roles on the HIGHEST warp ids: the issue arbiter favours them)
+// Pipelines (mbarrier):  wfull/wempty[WS]  TMA <-> dequant   (int8, 256 k per stage = two 128-byte-wide swizzled boxes)
+//                        xfull/xempty[XS]  TMA <-> MMA       (activations)
+//                        afull/aempty[2]   dequant <-> MMA   (A operand in TMEM, 256 k = 16 UMMAs per hand-off)
+//                        tfull/tempty[ND]  MMA <-> epilogue  (accumulator; double-buffered when BT <= 128, so the epilogue
+//                                                             of one segment overlaps the main loop of the next)
 //
 // Arithmetic.  fp16: A = fp16(fp16(q) * s) with ONE rounding per weight and fp32 accumulation -- exactly the
 // reference's K1 arithmetic (mma_tensorop_dequantizer.h:259-274, default_fpA_intB_traits.h:110), so results
 // match it up to fp32 summation order.  bf16 (extension): A = bf16(q) exactly, scale applied in the fp32 epilogue.
 //
-// Small M is HBM-bound and N/128 tiles do not fill 148 SMs, so K is split over `splits` CTAs per tile; partial
-// tiles go through an fp32 workspace; the `splits` CTAs of a tile meet at a counter and each reduces its share of
-// the token columns in split order (deterministic); the last to leave resets the counters, so the workspace needs
-// zeroing only once (the reference disables split-K
-// altogether by passing a null workspace, fpA_intB_gemm_wrapper.cu:169-170).
-//
 // Roofline: bytes = K*N + 2N + 2MK + 2MN, flops = 2MNK; HBM-bound for M <~ 140, tensor-bound above.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -44,38 +51,34 @@ namespace eetq_b200 {
 
 namespace {
 
-constexpr int BLOCK_N      = 128;  // output features per CTA  (UMMA M)
-constexpr int BLOCK_K      = 64;   // k per pipeline stage (64 fp16 = one 128-byte swizzle row)
+constexpr int BLOCK_N      = 128;  // output features per tile  (UMMA M)
+constexpr int STAGE_K      = 256;  // k per weight stage / per A operand stage (one dequant -> MMA hand-off)
+constexpr int SUB_K        = 64;   // k per activation TMA box (64 fp16 = one 128-byte swizzle row)
+constexpr int SUBS         = STAGE_K / SUB_K;
 constexpr int UMMA_K       = 16;
-constexpr int NUM_A_STAGES = 4;   // fp16 A tiles in flight between the dequant groups and the MMA issuer
-constexpr int DQ_GROUPS    = 2;   // dequant warps work as 2 groups of 4 warps on alternating k-blocks
-constexpr int DQ_WARPS     = 8;
-constexpr int DQ_THREADS   = DQ_WARPS * 32;
-constexpr int TC_THREADS   = 64 + DQ_THREADS + 32;  // warp 0 weight TMA, warp 1 MMA, 8 dequant/epilogue warps, warp 10 activation TMA
-// Role -> warp mapping: the single-thread roles get the HIGHEST warp ids (the SM's issue arbiter favours higher warp
-// ids among eligible warps of a sub-partition, so the MMA issuer and the TMA producers are never starved by dequant warps)
-constexpr int W_PRODUCER_WARP = DQ_WARPS;      // 8
-constexpr int MMA_WARP        = DQ_WARPS + 1;  // 9
-constexpr int X_PRODUCER_WARP = DQ_WARPS + 2;  // 10
-constexpr int W8_TILE      = BLOCK_N * BLOCK_K;       // 8192 B of int8
-constexpr int A_TILE       = BLOCK_N * BLOCK_K * 2;   // 16384 B of fp16/bf16
+constexpr int W_BOX_BYTES  = BLOCK_N * 128;       // one 128-byte-wide swizzled int8 box = 16 KB
+constexpr int W_STAGE      = 2 * W_BOX_BYTES;     // 32 KB
+constexpr int A_STAGES     = 2;
+constexpr int A_STAGE_COLS = STAGE_K / 2;         // 128 TMEM columns (two 16-bit values per 32-bit column)
+constexpr int A_COL0       = 256;                 // TMEM columns [256, 512) hold the A ring, [0, 256) the accumulators
+constexpr int TMEM_COLS    = 512;
+constexpr int EPI_WARPS    = 4;
+constexpr int EPI_THREADS  = EPI_WARPS * 32;
+constexpr int kFlagRegionBytes = 4096;            // one int flag per CTA (<= 1024 CTAs)
+constexpr int TRACE_SLOTS  = 64;
 
-// The int8 weights are staged 256 k-bytes at a time (one 256-byte-wide TMA box per stage): the b200
-// layout is row-major, so a 64-byte-wide box would touch 128 DRAM pages for 8 KB -- 256 contiguous bytes per row is the
-// widest box TMA allows for 1-byte elements.  Each weight stage therefore feeds 4 consecutive 64-k MMA blocks; the
-// activation tiles keep their own (64-k) stage ring.
-constexpr int W_SUB          = 4;                       // 64-k sub-blocks per weight stage
-constexpr int W_STAGE        = W_SUB * W8_TILE;         // 32 KB
-constexpr int W_HALF         = BLOCK_N * 128;           // one 128-byte-wide swizzled box = 16 KB
-__host__ __device__ constexpr int w_stages_for(int bt) { return bt >= 256 ? 2 : (bt >= 64 ? 3 : 4); }
-__host__ __device__ constexpr int x_stages_for(int bt) { return bt >= 256 ? 3 : (bt >= 128 ? 3 : (bt >= 64 ? 4 : 6)); }
-__host__ __device__ constexpr int x_tile_bytes(int bt) { return bt * BLOCK_K * 2; }
+__host__ __device__ constexpr int tc_threads(int dqw) { return (EPI_WARPS + dqw + 3) * 32; }
+__host__ __device__ constexpr int w_stages_for(int bt) { return bt <= 64 ? 5 : (bt <= 128 ? 4 : 3); }
+// activation ring: for small token tiles one ring stage carries all four 64-k boxes of a weight stage (one wait per
+// hand-off); for large tiles a stage is a single 64-k box
+__host__ __device__ constexpr int x_sub_for(int bt) { return bt <= 32 ? 4 : 1; }
+__host__ __device__ constexpr int x_stages_for(int bt) { return bt <= 16 ? 4 : (bt <= 32 ? 3 : (bt <= 64 ? 6 : (bt <= 128 ? 4 : 3))); }
+__host__ __device__ constexpr int x_stage_bytes(int bt) { return x_sub_for(bt) * bt * SUB_K * 2; }
 __host__ __device__ constexpr int smem_bytes_for(int bt)
 {
-    return 1024 /*alignment slack*/ + w_stages_for(bt) * W_STAGE + x_stages_for(bt) * x_tile_bytes(bt) + NUM_A_STAGES * A_TILE
-           + 512 /*barriers*/;
+    return 1024 /*alignment slack*/ + w_stages_for(bt) * W_STAGE + x_stages_for(bt) * x_stage_bytes(bt) + 512 /*barriers*/;
 }
-__host__ __device__ constexpr int tmem_cols_for(int bt) { return bt < 32 ? 32 : bt; }
+__host__ __device__ constexpr int acc_buffers_for(int bt) { return bt <= 128 ? 2 : 1; }
 
 // ------------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -107,7 +110,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -136,16 +138,16 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (fp16 or bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, kind::f16 (fp16 or bf16 inputs, fp32 accumulate), A operand read from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
@@ -159,6 +161,31 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 32 consecutive 32-bit columns <- 32 registers per thread (the dequantised A operand: 64 fp16/bf16 per lane)
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major; 1) |
@@ -183,15 +210,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int is_bf16, int umma_m, int u
 }
 
 // ------------------------------------------------------------------------------------------------- dequant
-// 16 int8 (one uint4) -> 16 fp16/bf16 (two uint4).
-//   fp16: PRMT each (biased) byte under the exponent of 1024 -> 1024+u, subtract 1152 -> q exactly,
+// 16 int8 (one uint4 of biased bytes u = q + 128, b200 layout) -> 16 fp16/bf16 in 8 registers, k order preserved.
+//   fp16: PRMT each byte under the exponent of 1024 -> 1024+u, subtract 1152 -> q exactly,
 //         multiply by the channel scale in fp16 (one rounding) == reference arithmetic.
 //   bf16: PRMT into the mantissa of 2^23 (fp32), subtract, pack to bf16 (exact: |q| <= 128).
 template <typename T>
-__device__ __forceinline__ void dequant16(const uint4& in, uint32_t scale2, uint4& out0, uint4& out1)
+__device__ __forceinline__ void dequant16(const uint4& in, uint32_t scale2, uint32_t* o)
 {
-    const uint32_t w[4] = {in.x, in.y, in.z, in.w};  // biased bytes u = q + 128 (b200 layout)
-    uint32_t o[8];
+    const uint32_t w[4] = {in.x, in.y, in.z, in.w};
     if constexpr (DTypeOf<T>::value == EETQ_B200_F16) {
         const __half2 bias = __half2half2(__ushort_as_half(0x6480));  // 1152
         const __half2 s2   = *reinterpret_cast<const __half2*>(&scale2);
@@ -214,66 +240,105 @@ __device__ __forceinline__ void dequant16(const uint4& in, uint32_t scale2, uint
             const float f1 = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7651)) - 8388736.f;
             const float f2 = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7652)) - 8388736.f;
             const float f3 = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7653)) - 8388736.f;
-            __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1);
-            __nv_bfloat162 hi = __floats2bfloat162_rn(f2, f3);
-            o[2 * i]     = *reinterpret_cast<uint32_t*>(&lo);
-            o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&hi);
+            // q is an integer with at most 8 significant bits: the upper half of its fp32 pattern IS its bf16 pattern
+            o[2 * i]     = __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
+            o[2 * i + 1] = __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632);
         }
     }
-    out0 = make_uint4(o[0], o[1], o[2], o[3]);
-    out1 = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 struct TcParams {
     const void* scales;
     const void* bias;
+    const void* residual;  // optional [M, N] added to the output in the epilogue (row stride ldr)
+    int64_t ldr;
     void* y;
     int64_t ldy;
     int M, N, K;
-    int splits;
-    int* tile_counters;   // [n_tiles * t_tiles], zero on entry, zero on exit
-    float* partials;      // [splits][n_tiles * t_tiles][BT][128]
+    int n_tiles, t_tiles;
+    int spt;           // 256-k stages per tile
+    int total_units;   // tiles * spt
+    int tile_aligned;  // 1: every CTA owns whole tiles (no workspace needed)
+    int* flags;        // [grid] zero on entry, zero on exit
+    float* slots;      // [grid][BT][128] fp32 partial tiles
+    unsigned long long* trace;  // optional [grid][TRACE_SLOTS] clock samples (instrumented build only)
 };
 
+__device__ __forceinline__ int unit_begin(const TcParams& p, int g, int G)
+{
+    if (p.tile_aligned) {
+        const int tiles = p.n_tiles * p.t_tiles;
+        return int((int64_t(g) * tiles) / G) * p.spt;
+    }
+    return int((int64_t(g) * p.total_units) / G);
+}
+
+__device__ __forceinline__ unsigned long long clk64()
+{
+    unsigned long long c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+    return c;
+}
+__device__ __forceinline__ unsigned long long gtime_ns()
+{
+    unsigned long long c;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(c));
+    return c;
+}
+
 // ------------------------------------------------------------------------------------------------- kernel
-template <typename T, int BT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <typename T, int BT, int DQW, bool TRACE>
+__global__ void __launch_bounds__(tc_threads(DQW), 1)
     w8a16_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p)
 {
-    constexpr int WS         = w_stages_for(BT);
-    constexpr int XS         = x_stages_for(BT);
-    constexpr int X_TILE     = x_tile_bytes(BT);
-    constexpr int TMEM_COLS  = tmem_cols_for(BT);
+    constexpr int WS          = w_stages_for(BT);
+    constexpr int XS          = x_stages_for(BT);
+    constexpr int XSUB        = x_sub_for(BT);      // 64-k boxes per activation ring stage
+    constexpr int XSTEPS      = SUBS / XSUB;        // activation ring stages per weight stage
+    constexpr int X_STAGE     = x_stage_bytes(BT);
+    constexpr int X_BOX       = BT * SUB_K * 2;
+    constexpr int ND          = acc_buffers_for(BT);
     constexpr bool SCALE_IN_A = DTypeOf<T>::value == EETQ_B200_F16;
-    constexpr uint32_t IDESC = make_idesc(DTypeOf<T>::value == EETQ_B200_BF16, BLOCK_N, BT);
+    constexpr uint32_t IDESC  = make_idesc(DTypeOf<T>::value == EETQ_B200_BF16, BLOCK_N, BT);
+    constexpr int NP          = DQW / 4;            // dequant warps per TMEM lane quadrant: each takes 1/NP of a stage's k
+    constexpr int CH          = 16 / NP;            // 16-byte chunks per thread per stage (8 or 4)
+    constexpr int W_PRODUCER_WARP = EPI_WARPS + DQW;
+    constexpr int MMA_WARP        = EPI_WARPS + DQW + 1;
+    constexpr int X_PRODUCER_WARP = EPI_WARPS + DQW + 2;
+    static_assert(DQW == 8 || DQW == 16, "8 or 16 dequant warps");
+    static_assert(ND * BT <= A_COL0, "accumulators must fit below the A ring");
 
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t w8_base   = smem_base;                                   // WS x 32 KB (two swizzled 16 KB halves each)
-    const uint32_t x_base    = w8_base + WS * W_STAGE;                       // XS x X_TILE
-    const uint32_t a_base    = x_base + XS * X_TILE;                         // 4 x 16 KB
-    const uint32_t bar_base  = a_base + NUM_A_STAGES * A_TILE;
-    const uint32_t wfull_bar  = bar_base;                 // WS x 8
-    const uint32_t wempty_bar = wfull_bar + WS * 8;       // WS x 8
-    const uint32_t xfull_bar  = wempty_bar + WS * 8;      // XS x 8
-    const uint32_t xempty_bar = xfull_bar + XS * 8;       // XS x 8
-    const uint32_t afull_bar  = xempty_bar + XS * 8;      // 4 x 8
-    const uint32_t aempty_bar = afull_bar + NUM_A_STAGES * 8;
-    const uint32_t tfull_bar = aempty_bar + NUM_A_STAGES * 8;
-    const uint32_t tmem_holder = tfull_bar + 8;
-    const uint32_t flag_holder = tmem_holder + 4;
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));         // generic pointer to smem_base
+    const uint32_t smem_base  = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w8_base    = smem_base;                      // WS x 32 KB (two 16 KB swizzled boxes each)
+    const uint32_t x_base     = w8_base + WS * W_STAGE;          // XS x X_STAGE
+    const uint32_t bar_base   = x_base + XS * X_STAGE;
+    const uint32_t wfull_bar  = bar_base;
+    const uint32_t wempty_bar = wfull_bar + WS * 8;
+    const uint32_t xfull_bar  = wempty_bar + WS * 8;
+    const uint32_t xempty_bar = xfull_bar + XS * 8;
+    const uint32_t afull_bar  = xempty_bar + XS * 8;
+    const uint32_t aempty_bar = afull_bar + A_STAGES * 8;
+    const uint32_t tfull_bar  = aempty_bar + A_STAGES * 8;
+    const uint32_t tempty_bar = tfull_bar + 2 * 8;
+    const uint32_t tmem_holder = tempty_bar + 2 * 8;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to smem_base
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int g    = blockIdx.x;
+    const int G    = gridDim.x;
+    const int u0   = unit_begin(p, g, G);
+    const int u1   = unit_begin(p, g + 1, G);
 
-    const int n_tile = blockIdx.x;
-    const int t_tile = blockIdx.y;
-    const int split  = blockIdx.z;
-    const int kb_total = p.K / BLOCK_K;
-    const int kb_begin = int((int64_t(split) * kb_total) / p.splits);
-    const int kb_end   = int((int64_t(split + 1) * kb_total) / p.splits);
-    const int num_kb   = kb_end - kb_begin;
+    unsigned long long* tr = nullptr;
+    if constexpr (TRACE) {
+        tr = p.trace + size_t(g) * TRACE_SLOTS;
+        if (threadIdx.x == 0) {
+            tr[48] = gtime_ns();
+            tr[49] = clk64();
+        }
+    }
 
     // ------------------------------------------------------------------ one-time setup
     if (warp == W_PRODUCER_WARP && lane == 0) {
@@ -281,17 +346,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tma_prefetch_desc(&map_x);
         for (int s = 0; s < WS; ++s) {
             mbar_init(wfull_bar + 8 * s, 1);
-            mbar_init(wempty_bar + 8 * s, DQ_WARPS);  // every dequant warp reads two sub-blocks of each weight stage
+            mbar_init(wempty_bar + 8 * s, DQW);
         }
         for (int s = 0; s < XS; ++s) {
             mbar_init(xfull_bar + 8 * s, 1);
             mbar_init(xempty_bar + 8 * s, 1);
         }
-        for (int a = 0; a < NUM_A_STAGES; ++a) {
-            mbar_init(afull_bar + 8 * a, DQ_WARPS / DQ_GROUPS);  // one elected arrive per warp of the owning group
+        for (int a = 0; a < A_STAGES; ++a) {
+            mbar_init(afull_bar + 8 * a, DQW);
             mbar_init(aempty_bar + 8 * a, 1);
         }
-        mbar_init(tfull_bar, 1);
+        for (int d = 0; d < 2; ++d) {
+            mbar_init(tfull_bar + 8 * d, 1);
+            mbar_init(tempty_bar + 8 * d, EPI_WARPS);
+        }
         fence_barrier_init();
     }
     if (warp == MMA_WARP)
@@ -302,228 +370,298 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_holder - smem_base));
 
     pdl_launch_dependents();
-    pdl_wait_prior_grids();  // x (and y / workspace) may be produced by the previous kernel in the stream
+    if constexpr (TRACE) {
+        if (threadIdx.x == 0)
+            tr[50] = clk64();
+    }
 
     if (warp == W_PRODUCER_WARP) {
-        // ============================================================== TMA producer
+        // ============================================================== weight TMA producer
+        // Weights never depend on the previous kernel in the stream: no griddepcontrol.wait here, the stream starts at once
         if (lane == 0) {
-            // weight stream: free-running (bounded only by its own ring), one 256-k stage per 4 MMA k-blocks
-            for (int wi = 0; wi * W_SUB < num_kb; ++wi) {
-                const int k0       = (kb_begin + wi * W_SUB) * BLOCK_K;
-                const int ws       = wi % WS;
-                const uint32_t wph = (wi / WS) & 1;
-                mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
-                mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
-                // k beyond K is zero-filled by TMA (and never converted: sub-blocks past num_kb are skipped)
-                tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, k0, n_tile * BLOCK_N);
+            int wcount = 0;
+            for (int u = u0; u < u1;) {
+                const int tile   = u / p.spt;
+                const int s0     = u - tile * p.spt;
+                const int s1     = min(p.spt, s0 + (u1 - u));
+                const int n_tile = tile % p.n_tiles;
+                for (int st = s0; st < s1; ++st, ++wcount) {
+                    const int ws       = wcount % WS;
+                    const uint32_t wph = (wcount / WS) & 1;
+                    mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
+                    mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
+                    // k beyond K (last stage when K % 256 != 0) is zero-filled by TMA; the matching activations are
+                    // zero-filled too, so those products vanish
+                    tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, st * STAGE_K, n_tile * BLOCK_N);
+                    tma_load_2d(w8_base + ws * W_STAGE + W_BOX_BYTES, &map_w, wfull_bar + 8 * ws, st * STAGE_K + 128, n_tile * BLOCK_N);
+                    if constexpr (TRACE) {
+                        if (wcount == 0) tr[51] = clk64();
+                    }
+                }
+                u += s1 - s0;
             }
         }
     }
     else if (warp == X_PRODUCER_WARP) {
-        // ============================================================== activation TMA producer (own warp, so a full
-        // activation ring never stalls the weight prefetch)
+        // ============================================================== activation TMA producer
         if (lane == 0) {
-            for (int it = 0; it < num_kb; ++it) {
-                const int k0       = (kb_begin + it) * BLOCK_K;
-                const int xs       = it % XS;
-                const uint32_t xph = (it / XS) & 1;
-                mbar_wait(xempty_bar + 8 * xs, xph ^ 1);
-                mbar_arrive_expect_tx(xfull_bar + 8 * xs, X_TILE);
-                tma_load_2d(x_base + xs * X_TILE, &map_x, xfull_bar + 8 * xs, k0, t_tile * BT);
+            pdl_wait_prior_grids();  // x may be produced by the previous kernel in the stream
+            int xcount = 0;
+            for (int u = u0; u < u1;) {
+                const int tile   = u / p.spt;
+                const int s0     = u - tile * p.spt;
+                const int s1     = min(p.spt, s0 + (u1 - u));
+                const int t_tile = tile / p.n_tiles;
+                for (int st = s0; st < s1; ++st) {
+#pragma unroll 1
+                    for (int xi = 0; xi < XSTEPS; ++xi, ++xcount) {
+                        const int xs       = xcount % XS;
+                        const uint32_t xph = (xcount / XS) & 1;
+                        mbar_wait(xempty_bar + 8 * xs, xph ^ 1);
+                        mbar_arrive_expect_tx(xfull_bar + 8 * xs, X_STAGE);
+#pragma unroll
+                        for (int j = 0; j < XSUB; ++j)
+                            tma_load_2d(x_base + xs * X_STAGE + j * X_BOX, &map_x, xfull_bar + 8 * xs,
+                                        st * STAGE_K + (xi * XSUB + j) * SUB_K, t_tile * BT);
+                    }
+                }
+                u += s1 - s0;
             }
         }
     }
     else if (warp == MMA_WARP) {
         // ============================================================== MMA issuer (one thread)
         if (lane == 0) {
-            for (int it = 0; it < num_kb; ++it) {
-                const int s       = it % XS;
-                const uint32_t ph = (it / XS) & 1;
-                const int a       = it % NUM_A_STAGES;
-                const uint32_t aph = (it / NUM_A_STAGES) & 1;
-                mbar_wait(xfull_bar + 8 * s, ph);     // activation tile landed
-                mbar_wait(afull_bar + 8 * a, aph);    // dequantised weight tile written
+            int acount = 0, xcount = 0, seg = 0;
+            for (int u = u0; u < u1; ++seg) {
+                const int tile = u / p.spt;
+                const int s0   = u - tile * p.spt;
+                const int s1   = min(p.spt, s0 + (u1 - u));
+                const int d    = seg % ND;
+                mbar_wait(tempty_bar + 8 * d, ((seg / ND) & 1) ^ 1);  // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t a_desc = make_kmajor_sw128_desc(a_base + a * A_TILE);
-                const uint64_t b_desc = make_kmajor_sw128_desc(x_base + s * X_TILE);
+                const uint32_t d_addr = tmem_base + uint32_t(d * BT);
+                for (int st = s0; st < s1; ++st, ++acount) {
+                    const int a        = acount % A_STAGES;
+                    const uint32_t aph = (acount / A_STAGES) & 1;
+                    mbar_wait(afull_bar + 8 * a, aph);  // 256 k of dequantised weights sit in TMEM
+                    tc_fence_after();
+                    const uint32_t a_addr = tmem_base + uint32_t(A_COL0 + a * A_STAGE_COLS);
+#pragma unroll 1
+                    for (int xi = 0; xi < XSTEPS; ++xi, ++xcount) {
+                        const int xs       = xcount % XS;
+                        const uint32_t xph = (xcount / XS) & 1;
+                        mbar_wait(xfull_bar + 8 * xs, xph);  // activation boxes landed
+                        tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (>>4) address field
-                    umma_f16(tmem_base, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                        for (int j = 0; j < XSUB; ++j) {
+                            const int sub         = xi * XSUB + j;
+                            const uint64_t b_desc = make_kmajor_sw128_desc(x_base + xs * X_STAGE + j * X_BOX);
+#pragma unroll
+                            for (int k = 0; k < SUB_K / UMMA_K; ++k) {
+                                // A: 16 k = 8 TMEM columns per UMMA; B: +32 bytes inside the swizzle atom = +2 in the (>>4) field
+                                umma_f16_ts(d_addr, a_addr + uint32_t(sub * (SUB_K / 2) + k * (UMMA_K / 2)), b_desc + uint64_t(2 * k), IDESC,
+                                            (st > s0 || sub > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(xempty_bar + 8 * xs);  // frees the activation stage once these MMAs have read it
+                    }
+                    umma_commit(aempty_bar + 8 * a);      // frees the A stage
+                    if constexpr (TRACE) {
+                        if (acount < 12) tr[16 + acount] = clk64();
+                    }
                 }
-                umma_commit(xempty_bar + 8 * s);    // frees the activation stage
-                umma_commit(aempty_bar + 8 * a);    // frees the A stage
+                umma_commit(tfull_bar + 8 * d);  // accumulator of this segment complete
+                u += s1 - s0;
             }
-            umma_commit(tfull_bar);                  // accumulator complete
+            if constexpr (TRACE) tr[30] = clk64();
+        }
+    }
+    else if (warp >= EPI_WARPS) {
+        // ============================================================== dequantisers: smem int8 -> registers -> TMEM
+        const int dw   = warp - EPI_WARPS;   // 0 .. DQW-1
+        const int quad = dw & 3;             // == warp % 4: the TMEM lane quadrant this warp may touch
+        const int part = dw >> 2;            // which 1/NP of the stage's k range
+        const int row  = quad * 32 + lane;   // feature row inside the tile
+        constexpr int CHUNK0 = 0;            // silence unused warnings in some instantiations
+        (void)CHUNK0;
+        const int c_first = part * CH;                    // first 16-byte chunk (of 16 per 256-k row)
+        const int box     = c_first >> 3;                 // which 128-byte-wide box
+        const int cb      = c_first & 7;                  // first chunk inside the box
+        const uint32_t row_off = uint32_t(box * W_BOX_BYTES + row * 128);
+        const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+        int wcount = 0, acount = 0;
+        for (int u = u0; u < u1;) {
+            const int tile   = u / p.spt;
+            const int s0     = u - tile * p.spt;
+            const int s1     = min(p.spt, s0 + (u1 - u));
+            const int n_tile = tile % p.n_tiles;
+            uint32_t scale2  = 0;
+            if constexpr (SCALE_IN_A) {
+                const int n      = n_tile * BLOCK_N + row;
+                const __half sv  = (n < p.N) ? static_cast<const __half*>(p.scales)[n] : __ushort_as_half(0);
+                const __half2 s2 = __half2half2(sv);
+                scale2           = *reinterpret_cast<const uint32_t*>(&s2);
+            }
+            for (int st = s0; st < s1; ++st, ++wcount, ++acount) {
+                const int ws       = wcount % WS;
+                const uint32_t wph = (wcount / WS) & 1;
+                const int a        = acount % A_STAGES;
+                const uint32_t aph = (acount / A_STAGES) & 1;
+                mbar_wait(wfull_bar + 8 * ws, wph);  // int8 stage landed
+                const uint8_t* rp = smem_gen + (w8_base - smem_base) + ws * W_STAGE + row_off;
+                uint4 in[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    in[j] = *reinterpret_cast<const uint4*>(rp + ((((cb + j) ^ (row & 7))) << 4));  // 128B swizzle: chunk ^ (row & 7)
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(wempty_bar + 8 * ws);  // bytes are in registers: hand the stage back to the TMA producer
+                mbar_wait(aempty_bar + 8 * a, aph ^ 1);  // the MMAs that read this A stage have completed
+                tc_fence_after();
+                const uint32_t a_col = uint32_t(A_COL0 + a * A_STAGE_COLS + c_first * 8);
+#pragma unroll
+                for (int h = 0; h < CH / 4; ++h) {
+                    uint32_t o[32];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dequant16<T>(in[h * 4 + j], scale2, &o[8 * j]);
+                    tmem_st_x32(tmem_base + lane_addr + a_col + uint32_t(h * 32), o);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(afull_bar + 8 * a);
+                if constexpr (TRACE) {
+                    if (dw == 0 && lane == 0 && acount < 12) tr[acount] = clk64();
+                }
+            }
+            u += s1 - s0;
         }
     }
     else {
-        // ============================================================== dequantisers, then epilogue
-        const int dt = threadIdx.x;       // 0..255 (warps 0..7)
-        // Two groups of 4 warps convert alternating k-blocks, so one group's smem round trips and barrier hops overlap
-        // the other's; inside a group every thread batches its 4 LDS.128 before converting (ILP) and each warp
-        // signals the MMA issuer with ONE elected mbarrier arrive.
-        constexpr int GROUP_THREADS     = DQ_THREADS / DQ_GROUPS;             // 128
-        constexpr int CHUNKS_PER_THREAD = (W8_TILE / 16) / GROUP_THREADS;     // 4
-        const int grp = dt / GROUP_THREADS;
-        const int gt  = dt % GROUP_THREADS;
-        // this thread always converts the same rows: fetch their channel scales once
-        uint32_t scale2[CHUNKS_PER_THREAD];
-#pragma unroll
-        for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
-            scale2[j] = 0;
-            if constexpr (SCALE_IN_A) {
-                const int n      = n_tile * BLOCK_N + ((gt + GROUP_THREADS * j) >> 2);
-                const __half sv  = (n < p.N) ? static_cast<const __half*>(p.scales)[n] : __ushort_as_half(0);
-                const __half2 s2 = __half2half2(sv);
-                scale2[j]        = *reinterpret_cast<const uint32_t*>(&s2);
-            }
-        }
-        for (int it = grp; it < num_kb; it += DQ_GROUPS) {
-            const int wi       = it / W_SUB;
-            const int sub_k    = it % W_SUB;          // which 64-k slice of the 256-k weight stage
-            const int ws       = wi % WS;
-            const uint32_t wph = (wi / WS) & 1;
-            const int a        = it % NUM_A_STAGES;
-            const uint32_t aph = (it / NUM_A_STAGES) & 1;
-            mbar_wait(wfull_bar + 8 * ws, wph);       // int8 stage landed
-            // stage = [128 rows][256 B] as ONE un-swizzled TMA box: 256-byte rows are the widest TMA allows for 1-byte
-            // elements and halve the number of DRAM requests per stage (the TMA unit, not HBM, bounds a weight stream
-            // made of 128-byte requests); the 2-way LDS bank conflict this costs is negligible next to that
-            const uint8_t* w8 = smem_gen + (w8_base - smem_base) + ws * W_STAGE;
-            uint8_t* at       = smem_gen + (a_base - smem_base) + a * A_TILE;
-            uint4 in[CHUNKS_PER_THREAD];
-#pragma unroll
-            for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
-                const int c   = gt + GROUP_THREADS * j;
-                const int row = c >> 2;
-                in[j] = *reinterpret_cast<const uint4*>(w8 + row * 256 + sub_k * 64 + (c & 3) * 16);
-            }
-            mbar_wait(aempty_bar + 8 * a, aph ^ 1);   // A stage free (the MMA that read it has completed)
-#pragma unroll
-            for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
-                const int c   = gt + GROUP_THREADS * j;  // 16-byte chunk index in the [128][64 B] slice
-                const int row = c >> 2;
-                const int kc  = c & 3;
-                uint4 o0, o1;
-                dequant16<T>(in[j], scale2[j], o0, o1);
-                // 128B swizzle: 16-byte chunk index XOR (row & 7)
-                uint8_t* rowp = at + row * 128;
-                *reinterpret_cast<uint4*>(rowp + (((2 * kc) ^ (row & 7)) << 4))     = o0;
-                *reinterpret_cast<uint4*>(rowp + (((2 * kc + 1) ^ (row & 7)) << 4)) = o1;
-            }
-            fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(afull_bar + 8 * a);
-                // the int8 bytes have been consumed (converted): after this group's last sub-block of the weight stage
-                // (sub-blocks 2 / 3, or its final k-block) hand the stage back to the TMA producer -- once per warp
-                if (sub_k >= W_SUB - DQ_GROUPS || it + DQ_GROUPS >= num_kb)
-                    mbar_arrive(wempty_bar + 8 * ws);
-            }
-        }
-
-        // ---------------------------------------------------------- epilogue
-        mbar_wait(tfull_bar, 0);
-        tc_fence_after();
-        const int quad   = warp & 3;                 // TMEM lane quadrant this warp may read
-        const int half_i = warp >> 2;                // two warps share a quadrant: split the columns
-        const int n      = n_tile * BLOCK_N + quad * 32 + lane;
-        const bool n_ok  = n < p.N;
-        constexpr int COLS_PER_WARP = BT / 2;        // BT >= 32 -> multiple of 16; BT == 16 handled below
-        constexpr int CHUNK = 16;
-        const int col_begin = (BT >= 32) ? half_i * COLS_PER_WARP : 0;
-        const int col_end   = (BT >= 32) ? col_begin + COLS_PER_WARP : ((half_i == 0) ? BT : 0);
-
-        float scale_f = 1.f, bias_f = 0.f;
-        if (n_ok) {
-            if constexpr (!SCALE_IN_A)
-                scale_f = to_float(static_cast<const T*>(p.scales)[n]);
-            if (p.bias != nullptr)
-                bias_f = to_float(static_cast<const T*>(p.bias)[n]);
-        }
+        // ============================================================== epilogue warps 0..3 (TMEM lane quadrant = warp)
+        const int quad = warp;
+        const int row  = quad * 32 + lane;
+        const int et   = threadIdx.x;  // 0..127
+        pdl_wait_prior_grids();        // y / workspace may still be in use by the previous kernel in the stream
         T* y = static_cast<T*>(p.y);
-        const int tile_id = t_tile * gridDim.x + n_tile;
-
-        if (p.splits == 1) {
-            for (int c0 = col_begin; c0 < col_end; c0 += CHUNK) {
+        int seg = 0;
+        for (int u = u0; u < u1; ++seg) {
+            const int tile   = u / p.spt;
+            const int s0     = u - tile * p.spt;
+            const int s1     = min(p.spt, s0 + (u1 - u));
+            const int n_tile = tile % p.n_tiles;
+            const int t_tile = tile / p.n_tiles;
+            const int d      = seg % ND;
+            const int n      = n_tile * BLOCK_N + row;
+            const bool n_ok  = n < p.N;
+            const bool contributor = s0 > 0;                 // somebody else owns this tile: dump the partial
+            const bool owner_fixup = (s0 == 0) && (s1 < p.spt);  // we own it but others hold the rest of its k range
+            float scale_f = 1.f, bias_f = 0.f;
+            if (!contributor && n_ok) {
+                if constexpr (!SCALE_IN_A)
+                    scale_f = to_float(static_cast<const T*>(p.scales)[n]);
+                if (p.bias != nullptr)
+                    bias_f = to_float(static_cast<const T*>(p.bias)[n]);
+            }
+            // contributors of an owned tile: the CTAs g+1 .. g_last whose ranges start inside this tile
+            int g_last = g;
+            if (owner_fixup) {
+                const int tile_end = (tile + 1) * p.spt;
+                while (g_last + 1 < G && unit_begin(p, g_last + 1, G) < tile_end)
+                    ++g_last;
+            }
+            mbar_wait(tfull_bar + 8 * d, (seg / ND) & 1);
+            tc_fence_after();
+            if constexpr (TRACE) {
+                if (et == 0 && seg < 4) tr[32 + 2 * seg] = clk64();
+            }
+            if (owner_fixup) {
+                // wait (normally not at all: the contributors met this tile first) until every contributor has published
+                if (et > 0 && et <= g_last - g) {
+                    while (ld_acquire_gpu(p.flags + g + et) == 0) {
+                    }
+                }
+                epi_bar_sync();
+            }
+            float* my_slot = p.slots + size_t(g) * (BT * BLOCK_N);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BT; c0 += 16) {
                 uint32_t r[16];
-                tmem_ld_x16(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
+                tmem_ld_x16(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(d * BT + c0), r);
                 tmem_ld_wait();
+                if (c0 + 16 >= BT) {
+                    // all of this accumulator is in registers: let the MMA issuer reuse it for the next segment
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(tempty_bar + 8 * d);
+                }
+                if (contributor) {
 #pragma unroll
-                for (int j = 0; j < CHUNK; ++j) {
+                    for (int j = 0; j < 16; ++j)
+                        my_slot[(c0 + j) * BLOCK_N + row] = __uint_as_float(r[j]);
+                    continue;
+                }
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    v[j] = __uint_as_float(r[j]);
+                if (owner_fixup) {
+                    for (int gg = g + 1; gg <= g_last; ++gg) {  // ascending CTA index == ascending k: deterministic sum order
+                        const float* slot = p.slots + size_t(gg) * (BT * BLOCK_N) + c0 * BLOCK_N + row;
+                        float w[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            w[j] = __ldcg(slot + j * BLOCK_N);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] += w[j];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
                     const int t = t_tile * BT + c0 + j;
-                    if (n_ok && t < p.M)
-                        y[int64_t(t) * p.ldy + n] = from_float<T>(__uint_as_float(r[j]) * scale_f + bias_f);
+                    if (n_ok && t < p.M) {
+                        T o = from_float<T>(v[j] * scale_f + bias_f);
+                        if (p.residual != nullptr)
+                            o = from_float<T>(to_float(o) + to_float(static_cast<const T*>(p.residual)[int64_t(t) * p.ldr + n]));
+                        y[int64_t(t) * p.ldy + n] = o;
+                    }
                 }
             }
-        }
-        else {
-            // split-K: publish this CTA's partial tile, last arriver reduces in split order
-            float* my_part = p.partials + (int64_t(split) * (gridDim.x * gridDim.y) + tile_id) * (BT * BLOCK_N);
-            for (int c0 = col_begin; c0 < col_end; c0 += CHUNK) {
-                uint32_t r[16];
-                tmem_ld_x16(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j)
-                    my_part[(c0 + j) * BLOCK_N + quad * 32 + lane] = __uint_as_float(r[j]);
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
-            // All `splits` CTAs of this tile are co-resident (grid <= 148 CTAs, one per SM): meet at an arrive counter, then
-            // EVERY CTA reduces its own 1/splits share of the token columns (in split order -> deterministic) instead of
-            // leaving one CTA to walk the whole tile through a chain of dependent L2 round trips.
-            int* arrive = p.tile_counters + tile_id;
-            int* depart = p.tile_counters + 512 + tile_id;
-            if (dt == 0) {
-                atomicAdd(arrive, 1);
-                while (*reinterpret_cast<volatile int*>(arrive) < p.splits) {
-                }
+            if (contributor) {
                 __threadfence();
+                epi_bar_sync();
+                if (et == 0)
+                    st_release_gpu(p.flags + g, 1);
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
-            const int cs      = BT / p.splits;                 // columns reduced by this CTA (splits is a power of two <= 8)
-            const int my_c0   = split * cs;
-            const int per_grp = (cs >= 2) ? cs / 2 : cs;       // the two warps of a lane quadrant share the columns
-            const int c_begin = my_c0 + ((cs >= 2) ? half_i * per_grp : 0);
-            const int c_end   = (cs >= 2 || half_i == 0) ? c_begin + per_grp : c_begin;
-            const int64_t tile_stride = int64_t(gridDim.x) * gridDim.y * (BT * BLOCK_N);
-            const float* base = p.partials + int64_t(tile_id) * (BT * BLOCK_N) + quad * 32 + lane;
-            for (int c = c_begin; c < c_end; c += 4) {
-                float v[4][8];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int sp = 0; sp < 8; ++sp)
-                        v[u][sp] = (sp < p.splits && c + u < c_end) ? __ldcg(base + sp * tile_stride + (c + u) * BLOCK_N) : 0.f;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int sp = 0; sp < 8; ++sp)
-                        acc += v[u][sp];
-                    const int t = t_tile * BT + c + u;
-                    if (c + u < c_end && n_ok && t < p.M)
-                        y[int64_t(t) * p.ldy + n] = from_float<T>(acc * scale_f + bias_f);
-                }
+            else if (owner_fixup) {
+                epi_bar_sync();  // every epilogue thread has finished reading the slots
+                if (et > 0 && et <= g_last - g)
+                    p.flags[g + et] = 0;  // leave the workspace clean for the next call
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(DQ_THREADS) : "memory");
-            if (dt == 0) {
-                // last CTA to leave resets both counters so the workspace stays clean for the next call
-                if (atomicAdd(depart, 1) == p.splits - 1) {
-                    *reinterpret_cast<volatile int*>(arrive) = 0;
-                    *reinterpret_cast<volatile int*>(depart) = 0;
-                }
+            if constexpr (TRACE) {
+                if (et == 0 && seg < 4) tr[33 + 2 * seg] = clk64();
             }
+            u += s1 - s0;
         }
-        tc_fence_before();
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+    if constexpr (TRACE) {
+        if (threadIdx.x == 0) {
+            tr[52] = clk64();
+            tr[53] = gtime_ns();
+            tr[54] = (unsigned long long)(u1 - u0);
+        }
     }
 }
 
@@ -546,15 +684,21 @@ EncodeTiledFn get_encode_fn()
     return fn;
 }
 
+int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return (e != nullptr && e[0] != '\0') ? atoi(e) : dflt;
+}
+
 struct MapKey {
     const void* ptr;
     uint64_t d0, d1, stride;
     uint32_t b0, b1;
-    int dtype, swizzle;
+    int dtype, swizzle, device;
     bool operator==(const MapKey& o) const
     {
         return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1 && dtype == o.dtype
-               && swizzle == o.swizzle;
+               && swizzle == o.swizzle && device == o.device;
     }
 };
 struct MapKeyHash {
@@ -562,18 +706,22 @@ struct MapKeyHash {
     {
         size_t h = std::hash<const void*>()(k.ptr);
         auto mix = [&h](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.d0); mix(k.d1); mix(k.stride); mix(k.b0); mix(k.b1); mix(uint64_t(k.dtype)); mix(uint64_t(k.swizzle));
+        mix(k.d0); mix(k.d1); mix(k.stride); mix(k.b0); mix(k.b1); mix(uint64_t(k.dtype)); mix(uint64_t(k.swizzle)); mix(uint64_t(k.device));
         return h;
     }
 };
 
-// 2-D tensor map over a row-major [d1][d0] matrix (d0 contiguous) with row pitch `stride` bytes; cached.
+// 2-D tensor map over a row-major [d1][d0] matrix (d0 contiguous) with row pitch `stride` bytes.  A tensor map encodes
+// nothing but (address, shape, box): the cache key holds all of them plus the device, so a recycled address with the same
+// geometry yields the identical (still valid) descriptor.
 int get_tensor_map(const void* ptr, CUtensorMapDataType dt, int dtype_tag, uint64_t d0, uint64_t d1, uint64_t stride, uint32_t b0,
-                   uint32_t b1, CUtensorMapSwizzle swz, CUtensorMap* out)
+                   uint32_t b1, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo, CUtensorMap* out)
 {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    MapKey key{ptr, d0, d1, stride, b0, b1, dtype_tag, int(swz)};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    MapKey key{ptr, d0, d1, stride, b0, b1, dtype_tag, int(swz) | (int(promo) << 8), dev};
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = cache.find(key);
@@ -591,51 +739,74 @@ int get_tensor_map(const void* ptr, CUtensorMapDataType dt, int dtype_tag, uint6
     cuuint64_t strides[1] = {stride};
     cuuint32_t box[2]     = {b0, b1};
     cuuint32_t estr[2]    = {1, 1};
-    CUresult r = fn(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu, stride %llu, box %u x %u)", int(r),
                   (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)stride, b0, b1);
         return EETQ_B200_ECUDA;
     }
     std::lock_guard<std::mutex> lk(mu);
-    if (cache.size() > 4096)
+    if (cache.size() > 8192)
         cache.clear();
     cache.emplace(key, *out);
     return EETQ_B200_OK;
 }
 
 struct TcConfig {
-    int bt;        // tokens per CTA tile (UMMA N)
-    int n_tiles;   // ceil(N / 128)
-    int t_tiles;   // ceil(M / bt)
-    int splits;    // split-K factor
+    int bt;       // tokens per tile (UMMA N)
+    int n_tiles;  // ceil(N / 128)
+    int t_tiles;  // ceil(M / bt)
+    int spt;      // 256-k stages per tile
+    int grid;     // persistent CTAs
+    bool split;   // some tile is shared between CTAs (needs the workspace)
 };
 
-TcConfig choose_config(int64_t M, int64_t N, int64_t K)
+int resident_ctas()
 {
-    // One CTA per SM (smem), 148 slots.  Dequantisation work scales with the number of token tiles, so up to 256
-    // tokens ride in ONE tile and spare SMs are filled by splitting K; above that, 256-token tiles.
+    const DeviceInfo& di = device_info();
+    return di.ok ? di.sm_count : 148;  // 1 CTA per SM (shared memory); never launch more than can be resident
+}
+
+TcConfig choose_config(int64_t M, int64_t N, int64_t K, bool have_workspace)
+{
     TcConfig c{};
-    c.bt      = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
-    c.n_tiles = int((N + BLOCK_N - 1) / BLOCK_N);
-    c.t_tiles = int((M + c.bt - 1) / c.bt);
+    const int sms = resident_ctas();
+    c.n_tiles     = int((N + BLOCK_N - 1) / BLOCK_N);
+    c.spt         = int((K + STAGE_K - 1) / STAGE_K);
+    int bt        = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+    // dequantisation work scales with the number of token tiles, so up to 256 tokens ride in one tile -- unless the
+    // tiles are so few that every tile will be shared by several CTAs: then 128-token tiles keep the fp32 partials
+    // that travel through the workspace small and give the accumulator double buffering
+    if (bt == 256 && int64_t(c.n_tiles) * ((M + 255) / 256) * 2 <= sms && have_workspace)
+        bt = 128;
+    const int force_bt = env_int("EETQ_B200_TC_BT", 0);
+    if (force_bt == 16 || force_bt == 32 || force_bt == 64 || force_bt == 128 || force_bt == 256)
+        bt = force_bt;
+    c.bt            = bt;
+    c.t_tiles       = int((M + bt - 1) / bt);
     const int tiles = c.n_tiles * c.t_tiles;
-    const int kb    = int(K / BLOCK_K);
-    int s           = 148 / tiles;
-    const int max_s = kb / 8 > 0 ? kb / 8 : 1;  // at least 8 k-blocks (512 k) per split
-    if (s > max_s) s = max_s;
-    if (s > 8) s = 8;
-    if (s < 1) s = 1;
-    while (s & (s - 1)) --s;  // power of two: every split CTA reduces an equal share of the token columns
-    c.splits = s;
+    const int64_t U = int64_t(tiles) * c.spt;
+    if (have_workspace) {
+        // at least two stages per CTA when there is that much work, and never more than ~64 CTAs sharing one tile (the
+        // owner polls one flag per contributor with its 128 epilogue threads)
+        const int64_t min_units = (c.spt + 63) / 64 > 2 ? (c.spt + 63) / 64 : 2;
+        int64_t g = U >= min_units ? U / min_units : 1;
+        if (g > sms) g = sms;
+        c.grid  = int(g);
+        c.split = true;
+    }
+    else {
+        c.grid  = tiles < sms ? tiles : sms;
+        c.split = false;
+    }
     return c;
 }
 
-template <typename T, int BT>
+template <typename T, int BT, int DQW, bool TRACE>
 int launch_tc(const CUtensorMap& map_w, const CUtensorMap& map_x, const TcParams& p, const TcConfig& cfg, bool pdl, cudaStream_t stream)
 {
-    auto kernel = w8a16_gemm_tc_kernel<T, BT>;
+    auto kernel = w8a16_gemm_tc_kernel<T, BT, DQW, TRACE>;
     constexpr int smem = smem_bytes_for(BT);
     static bool attr_set[64] = {};
     int dev = 0;
@@ -645,8 +816,8 @@ int launch_tc(const CUtensorMap& map_w, const CUtensorMap& map_x, const TcParams
         attr_set[dev] = true;
     }
     cudaLaunchConfig_t lc{};
-    lc.gridDim          = dim3(unsigned(cfg.n_tiles), unsigned(cfg.t_tiles), unsigned(cfg.splits));
-    lc.blockDim         = dim3(TC_THREADS);
+    lc.gridDim          = dim3(unsigned(cfg.grid));
+    lc.blockDim         = dim3(tc_threads(DQW));
     lc.dynamicSmemBytes = smem;
     lc.stream           = stream;
     cudaLaunchAttribute attr[1];
@@ -663,72 +834,93 @@ int launch_tc(const CUtensorMap& map_w, const CUtensorMap& map_x, const TcParams
     return EETQ_B200_OK;
 }
 
-template <typename T>
+template <typename T, int DQW, bool TRACE>
 int launch_tc_bt(const CUtensorMap& map_w, const CUtensorMap& map_x, const TcParams& p, const TcConfig& cfg, bool pdl, cudaStream_t stream)
 {
     switch (cfg.bt) {
-        case 16: return launch_tc<T, 16>(map_w, map_x, p, cfg, pdl, stream);
-        case 32: return launch_tc<T, 32>(map_w, map_x, p, cfg, pdl, stream);
-        case 64: return launch_tc<T, 64>(map_w, map_x, p, cfg, pdl, stream);
-        case 128: return launch_tc<T, 128>(map_w, map_x, p, cfg, pdl, stream);
-        default: return launch_tc<T, 256>(map_w, map_x, p, cfg, pdl, stream);
+        case 16: return launch_tc<T, 16, DQW, TRACE>(map_w, map_x, p, cfg, pdl, stream);
+        case 32: return launch_tc<T, 32, DQW, TRACE>(map_w, map_x, p, cfg, pdl, stream);
+        case 64: return launch_tc<T, 64, DQW, TRACE>(map_w, map_x, p, cfg, pdl, stream);
+        case 128: return launch_tc<T, 128, DQW, TRACE>(map_w, map_x, p, cfg, pdl, stream);
+        default: return launch_tc<T, 256, DQW, TRACE>(map_w, map_x, p, cfg, pdl, stream);
     }
 }
-
-// The tile counters live in a FIXED-size region at the start of the workspace so that calls with different
-// (M, N, K) -- hence different partial-buffer layouts -- can share one zero-initialised workspace: only the counter
-// region must stay zero between calls, and every kernel leaves it zero.  Split-K is only chosen when
-// tiles <= 296, so 4 KiB (1024 counters) is always enough.
-constexpr size_t kCounterRegionBytes = 4096;
-size_t counters_bytes(const TcConfig&) { return kCounterRegionBytes; }
 
 }  // namespace
 
+// Workspace = [flag region][grid x BT x 128 fp32 partial slots].  The flag region must be ZERO before the first call;
+// every call leaves it zero (so one zero-initialised buffer serves all shapes and is only zeroed once).
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K)
 {
-    if (M <= 0 || N <= 0 || K < BLOCK_K)
+    if (M <= 0 || N <= 0 || K <= 0)
         return 0;
-    const TcConfig c = choose_config(M, N, K);
-    if (c.splits == 1)
-        return 0;
-    return counters_bytes(c) + size_t(c.splits) * c.n_tiles * c.t_tiles * c.bt * BLOCK_N * sizeof(float);
+    const TcConfig c = choose_config(M, N, K, true);
+    return size_t(kFlagRegionBytes) + size_t(c.grid) * c.bt * BLOCK_N * sizeof(float);
 }
 
-int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
-                   int64_t M, int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes, bool pdl,
-                   cudaStream_t stream)
+int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
+                   int64_t ldr, void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
+                   size_t workspace_bytes, bool pdl, unsigned long long* trace, cudaStream_t stream)
 {
-    TcConfig cfg = choose_config(M, N, K);
-    const size_t need = gemm_tc_workspace_bytes(M, N, K);
-    if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
-        // no (or too small a) workspace: fall back to a single split rather than failing
-        cfg.splits = 1;
+    const bool have_ws = workspace != nullptr && workspace_bytes >= gemm_tc_workspace_bytes(M, N, K);
+    // no (or too small a) workspace: every CTA takes whole tiles -- correct, just less evenly balanced
+    const TcConfig cfg = choose_config(M, N, K, have_ws);
+    if (cfg.grid > kFlagRegionBytes / int(sizeof(int))) {
+        set_error("gemm_tc: grid %d exceeds the flag region", cfg.grid);
+        return EETQ_B200_EINVAL;
     }
+    static const int promo_knob = env_int("EETQ_B200_TC_L2PROMO", 256);
+    const CUtensorMapL2promotion wpromo = promo_knob == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                         : promo_knob == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                            : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUtensorMap map_w, map_x;
-    if (int rc = get_tensor_map(w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 100, uint64_t(K), uint64_t(N), uint64_t(K), 256, BLOCK_N,
-                                CU_TENSOR_MAP_SWIZZLE_NONE, &map_w))
+    // weights: [N rows][K bytes]; one box = 128 rows x 128 bytes, 128B-swizzled so that the dequant warps' row-per-lane
+    // 16-byte reads are bank-conflict free; L2 promotion 256 B makes the two boxes of a stage one DRAM burst per row
+    if (int rc = get_tensor_map(w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 100, uint64_t(K), uint64_t(N), uint64_t(K), 128, BLOCK_N,
+                                CU_TENSOR_MAP_SWIZZLE_128B, wpromo, &map_w))
         return rc;
     const CUtensorMapDataType xdt = dtype == EETQ_B200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    if (int rc = get_tensor_map(x, xdt, dtype, uint64_t(K), uint64_t(M), uint64_t(ldx) * 2, BLOCK_K, uint32_t(cfg.bt),
-                                CU_TENSOR_MAP_SWIZZLE_128B, &map_x))
+    if (int rc = get_tensor_map(x, xdt, dtype, uint64_t(K), uint64_t(M), uint64_t(ldx) * 2, SUB_K, uint32_t(cfg.bt),
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, &map_x))
         return rc;
 
     TcParams p{};
-    p.scales = scales;
-    p.bias   = bias;
-    p.y      = y;
-    p.ldy    = ldy;
-    p.M      = int(M);
-    p.N      = int(N);
-    p.K      = int(K);
-    p.splits = cfg.splits;
-    if (cfg.splits > 1) {
-        p.tile_counters = static_cast<int*>(workspace);
-        p.partials      = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + counters_bytes(cfg));
+    p.scales       = scales;
+    p.bias         = bias;
+    p.residual     = residual;
+    p.ldr          = ldr;
+    p.y            = y;
+    p.ldy          = ldy;
+    p.M            = int(M);
+    p.N            = int(N);
+    p.K            = int(K);
+    p.n_tiles      = cfg.n_tiles;
+    p.t_tiles      = cfg.t_tiles;
+    p.spt          = cfg.spt;
+    p.total_units  = cfg.n_tiles * cfg.t_tiles * cfg.spt;
+    p.tile_aligned = cfg.split ? 0 : 1;
+    p.trace        = trace;
+    if (cfg.split) {
+        p.flags = static_cast<int*>(workspace);
+        p.slots = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kFlagRegionBytes);
+    }
+    static const int dqw = env_int("EETQ_B200_TC_DQW", 8);
+    if (trace != nullptr) {
+        if (dtype != EETQ_B200_F16) {
+            set_error("gemm_tc: the instrumented build exists for fp16 only");
+            return EETQ_B200_EINVAL;
+        }
+        return dqw == 16 ? launch_tc_bt<__half, 16, true>(map_w, map_x, p, cfg, pdl, stream)
+                         : launch_tc_bt<__half, 8, true>(map_w, map_x, p, cfg, pdl, stream);
     }
     if (dtype == EETQ_B200_F16)
-        return launch_tc_bt<__half>(map_w, map_x, p, cfg, pdl, stream);
-    return launch_tc_bt<__nv_bfloat16>(map_w, map_x, p, cfg, pdl, stream);
+        return dqw == 16 ? launch_tc_bt<__half, 16, false>(map_w, map_x, p, cfg, pdl, stream)
+                         : launch_tc_bt<__half, 8, false>(map_w, map_x, p, cfg, pdl, stream);
+    return dqw == 16 ? launch_tc_bt<__nv_bfloat16, 16, false>(map_w, map_x, p, cfg, pdl, stream)
+                     : launch_tc_bt<__nv_bfloat16, 8, false>(map_w, map_x, p, cfg, pdl, stream);
 }
+
+int gemm_tc_trace_slots() { return TRACE_SLOTS; }
+int gemm_tc_grid_for(int64_t M, int64_t N, int64_t K) { return choose_config(M, N, K, true).grid; }
 
 }  // namespace eetq_b200

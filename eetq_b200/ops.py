@@ -185,9 +185,11 @@ def _gemm_into(x2: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, bias
     L = _cabi.lib()
     ws_bytes = int(L.eetq_b200_workspace_bytes(M, N, K)) if M > 4 else 0
     ws = _workspace(x2.device, ws_bytes)
-    rc = L.eetq_b200_w8a16_gemm_ex(_vp(x2), x2.stride(0) if M > 0 else K, _vp(weight), _vp(scale), _vp(bias), _vp(out2),
-                                   out2.stride(0) if M > 0 else N, M, N, K, _DTYPE_CODE[x2.dtype], _vp(ws),
-                                   0 if ws is None else ws.numel(), flags, _stream())
+    # a single row has no meaningful row stride (torch allows anything there): pass the contiguous value
+    ldx = x2.stride(0) if M > 1 else K
+    ldy = out2.stride(0) if M > 1 else N
+    rc = L.eetq_b200_w8a16_gemm_ex(_vp(x2), ldx, _vp(weight), _vp(scale), _vp(bias), _vp(out2), ldy, M, N, K,
+                                   _DTYPE_CODE[x2.dtype], _vp(ws), 0 if ws is None else ws.numel(), flags, _stream())
     _cabi.check(rc, "eetq_b200_w8a16_gemm")
 
 

@@ -110,10 +110,10 @@ int eetq_b200_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t*
  *   w_b200 K*N int8 in b200 layout;  scales [N] dtype;  bias [N] dtype or NULL
  *   y [M,N] dtype, row stride ldy elements
  *   workspace: at least eetq_b200_workspace_bytes(M,N,K) bytes, ZERO-INITIALISED ONCE by the caller; its first
- *   4 KiB hold split-K tile counters that every call leaves at zero, the rest is scratch, so ONE buffer sized for
- *   the largest call can be reused by calls of any shape.  May be NULL when that function returns 0 (if it is
- *   NULL or too small otherwise, the call still succeeds without split-K).  One workspace must not be shared by
- *   calls that can run concurrently.
+ *   4 KiB hold the stream-K hand-off flags that every call leaves at zero, the rest is fp32 partial-tile scratch, so
+ *   ONE buffer sized for the largest call can be reused by calls of any shape.  If it is NULL or too small the call
+ *   still succeeds with whole tiles per CTA (no K splitting: slower for small M).  One workspace must not be shared
+ *   by calls that can run concurrently.
  * ------------------------------------------------------------------------------------------- */
 size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K);
 
@@ -123,6 +123,20 @@ int eetq_b200_w8a16_gemm(const void* x, const int8_t* w_b200, const void* scales
 int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
                             void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
                             size_t workspace_bytes, int flags, void* stream);
+
+/* Same as eetq_b200_w8a16_gemm_ex with a residual epilogue: y = dtype(dtype(acc * s [+ bias]) + residual[m, n]) (row stride ldr
+ * elements; `hidden = residual + o_proj(...)`).  The reference never wired FT's residual epilogues
+ * (fpA_intB_gemm_template.h:492-537) and adds the residual with a separate torch op. */
+int eetq_b200_w8a16_gemm_residual(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
+                                  const void* residual, int64_t ldr, void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype,
+                                  void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* Diagnostics (tools/tc_trace.py): runs the INSTRUMENTED build of the tcgen05 kernel (fp16), which records per-CTA clock
+ * samples of every pipeline role into `trace` ([grid][slots] uint64, sizes from eetq_b200_w8a16_gemm_trace_info). */
+int eetq_b200_w8a16_gemm_trace(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, void* y, int64_t ldy, int64_t M,
+                               int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* trace, size_t trace_bytes,
+                               void* stream);
+int eetq_b200_w8a16_gemm_trace_info(int64_t M, int64_t N, int64_t K, int* grid, int* slots);
 
 /* Convenience for hosts without their own device-memory plumbing: x_host / y_host are HOST buffers
  * (pinned for true async); the call stages them through the caller-provided device scratch

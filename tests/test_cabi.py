@@ -71,8 +71,11 @@ def test_empty_batch_is_ok_without_gpu(lib):
 
 def test_workspace_bytes(lib):
     assert lib.eetq_b200_workspace_bytes(1, 4096, 4096) >= 0
-    assert lib.eetq_b200_workspace_bytes(16, 4096, 4096) > 0       # split-K engaged for small M
-    assert lib.eetq_b200_workspace_bytes(1024, 4096, 4096) == 0    # enough tiles, no split
+    small = lib.eetq_b200_workspace_bytes(16, 4096, 4096)
+    big = lib.eetq_b200_workspace_bytes(1024, 4096, 4096)
+    # stream-K: 4 KiB of flags + one fp32 partial tile [tokens per tile x 128] per persistent CTA (<= one CTA per SM)
+    assert 4096 < small <= 4096 + 1024 * 16 * 128 * 4
+    assert small < big <= 4096 + 1024 * 256 * 128 * 4
     assert lib.eetq_b200_workspace_bytes(0, 4096, 4096) == 0
 
 

@@ -100,12 +100,14 @@ def main():
             print(json.dumps(r), flush=True)
             results.append(r)
             del wf
-        for M in ([] if args.gemv_only else [8, 16, 64, 256, 1024] if not args.quick else [16, 1024]):
+        for M in ([] if args.gemv_only else [8, 16, 64, 256, 1024] if not args.quick else [16, 256, 1024]):
             x = torch.randn(M, K, device=dev).half()
-            fns = [(lambda w=w: w8_a16_gemm_bias(x, w, sc, None, flags=_cabi.FLAG_FORCE_TC)) for w in ws]
+            tc_pdl = os.environ.get("KBENCH_TC_PDL", "0") == "1"
+            fns = [(lambda w=w: w8_a16_gemm_bias(x, w, sc, None, flags=_cabi.FLAG_FORCE_TC | (_cabi.FLAG_PDL if tc_pdl else 0))) for w in ws]
             med, best = time_graph(fns)
-            r = dict(kernel="gemm_tc", K=K, N=N, M=M, us=med, us_best=best, gbs=algo_bytes(M, N, K) / med / 1e3,
-                     tflops=2.0 * M * N * K / med / 1e6)
+            r = dict(kernel="gemm_tc", impl=os.environ.get("EETQ_B200_TC_IMPL", "v2"), dqw=os.environ.get("EETQ_B200_TC_DQW", "8"),
+                     l2promo=os.environ.get("EETQ_B200_TC_L2PROMO", "256"), pdl=bool(tc_pdl), K=K, N=N, M=M, us=med, us_best=best,
+                     gbs=algo_bytes(M, N, K) / med / 1e3, tflops=2.0 * M * N * K / med / 1e6)
             print(json.dumps(r), flush=True)
             results.append(r)
         del ws

@@ -45,6 +45,11 @@ def run(M, K, N, dtype=torch.float16, onehot=False):
 if __name__ == "__main__":
     torch.cuda.set_device(0)
     ok = True
+    if "--tiny" in sys.argv:   # compute-sanitizer target: a few small launches only
+        for (M, K, N) in [(16, 512, 256), (64, 1024, 384), (256, 1024, 256)]:
+            ok &= run(M, K, N) <= 1e-3
+        print("TC_DEBUG", "PASS" if ok else "FAIL")
+        sys.exit(0)
     for (M, K, N, oh) in [(16, 64, 128, True), (64, 64, 128, True), (16, 64, 128, False), (16, 128, 128, False), (16, 512, 256, False),
                           (32, 512, 256, False), (64, 1024, 256, False), (128, 1024, 256, False), (256, 1024, 256, False),
                           (300, 1024, 320, False), (16, 4096, 4096, False), (1024, 4096, 4096, False)]:
