@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeetq_b200.so")
-SOURCES = ["cabi.cu", "quantize.cu", "gemv.cu", "gemm_tc.cu", "decode_ops.cu"]
+SOURCES = ["cabi.cu", "quantize.cu", "gemv.cu", "gemv_mma.cu", "gemm_tc.cu", "decode_ops.cu"]
 # development only: EETQ_B200_BUILD_V1=1 also compiles the round-1 tcgen05 kernel as an A/B baseline (EETQ_B200_TC_IMPL=v1)
 if os.environ.get("EETQ_B200_BUILD_V1") == "1":
     SOURCES.append("gemm_tc_v1.cu")

@@ -190,6 +190,16 @@ bool use_v1()
 #endif
 }
 
+// EETQ_B200_GEMV_MMA=0 sends M = 2..8 back to the SIMT kernel (A/B measurements)
+bool gemv_mma_on()
+{
+    static const bool v = [] {
+        const char* e = getenv("EETQ_B200_GEMV_MMA");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return v;
+}
+
 int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias, const void* residual,
                   int64_t ldr, void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
                   size_t workspace_bytes, int flags, unsigned long long* trace, void* stream)
@@ -214,6 +224,8 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
         use_gemv = false;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (use_gemv && M >= 2 && gemv_mma_on() && gemv_mma_supported(int(M), K))
+        return launch_gemv_mma(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, pdl, s);
     if (use_gemv) {
         GemvExtras ex;
         ex.residual = residual;

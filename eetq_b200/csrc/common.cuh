@@ -102,6 +102,11 @@ struct GemvChainPhase {
 };
 int launch_gemv_chain(const GemvChainPhase* phases, int nphases, unsigned* counters, const int* epoch, bool pdl, cudaStream_t stream);
 
+// tensor-core (mma.sync) streaming kernel for 2 <= M <= 8 decode rows (gemv_mma.cu)
+bool gemv_mma_supported(int M, int64_t K);
+int launch_gemv_mma(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
+                    int64_t ldr, void* y, int64_t ldy, int M, int64_t N, int64_t K, int dtype, bool pdl, cudaStream_t stream);
+
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
                    int64_t ldr, void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,

@@ -70,13 +70,13 @@ def main():
         pool = max(2, (2 * L2_BYTES) // (K * N) + 1)
         ws = [torch.randint(-128, 128, (K, N), dtype=torch.int8, device=dev) for _ in range(pool)]
         sc = (torch.rand(N, device=dev) * 0.01).half()
-        for M in ([] if args.tc_only else [1, 2, 4] if not args.quick else [1]):
+        for M in ([] if args.tc_only else [1, 2, 3, 4] if not args.quick else [1]):
             x = torch.randn(M, K, device=dev).half()
             for mode, pdl in ((1, False), (1, True)):
                 flags = _cabi.FLAG_FORCE_GEMV | (_cabi.FLAG_PDL if pdl else 0)
                 fns = [(lambda w=w: w8_a16_gemm_bias(x, w, sc, None, flags=flags)) for w in ws]
                 med, best = time_graph(fns)
-                r = dict(kernel="gemv", K=K, N=N, M=M, cvt=mode, pdl=pdl, us=med, us_best=best,
+                r = dict(kernel="gemv", mma=os.environ.get("EETQ_B200_GEMV_MMA", "1") != "0" and M >= 2, K=K, N=N, M=M, pdl=pdl, us=med, us_best=best,
                          gbs=algo_bytes(M, N, K) / med / 1e3)
                 print(json.dumps(r), flush=True)
                 results.append(r)
