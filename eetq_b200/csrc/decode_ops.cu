@@ -1,11 +1,17 @@
-// decode_ops.cu -- decode-side glue kernels around the w8a16 GEMV: embedding gather,
-// RMSNorm, RoPE + KV-cache append, split-KV decode attention.  They exist so that the headline metric (Llama-2-7B
-// decode tokens/s) is not dominated by framework-op launch overhead; they are NOT part of the reference's hot-path
-// boundary.  Reference counterparts, for behaviour only:
-//   rotary_embedding_neox_kernel  /root/reference/csrc/embedding_kernels/pos_encoding_kernels.cu:12-53
-//   generalT5LayerNorm (RMSNorm)  /root/reference/csrc/layernorm_kernels/layernorm.cu:25-51
+// decode_ops.cu -- glue kernels either side of the w8a16 linears: embedding gather, RMSNorm,
+// RoPE + KV-cache append, decode attention, lm_head + greedy argmax, and the prefill-side element-wise pieces.  They exist so
+// that the headline metric (Llama-2-7B decode tokens/s) is bounded by the weight stream rather than by framework-op launches;
+// they are NOT part of the reference's w8a16 boundary.  Reference counterparts, for behaviour:
+//   rotary_embedding_neox_kernel  /root/reference/csrc/embedding_kernels/pos_encoding_kernels.cu:12-53   (also exported by name)
+//   generalT5LayerNorm            /root/reference/csrc/layernorm_kernels/layernorm.cu:25-51             (also exported by name)
 //   EETLlamaAttention (SDPA path) /root/reference/python/eetq/modules/llama_modules.py:68-149
-// All kernels are single-token (M = 1) decode kernels, fp16, launched with optional programmatic dependent launch.
+// fp16.  Decode kernels are single-token; every launch can carry the programmatic-dependent-launch attribute.
+//
+// Multi-GPU (column-sharded linears): vectors that every rank needs (attention output, residual stream,
+// MLP activation, arg-max candidates) travel as "LL" buffers -- each 8-byte word = {two fp16 values, 32-bit tag} stored with
+// one 8-byte store straight into every peer's copy over NVLink (symmetric memory).  A word is valid when its tag equals the
+// tag of the exchange (step counter x exchanges per step + exchange index), so data and flag arrive together: no fence, no
+// separate flag, no collective call, and the consumer's prologue simply polls the words it is about to use.
 #include "common.cuh"
 
 namespace eetq_b200 {
@@ -13,44 +19,64 @@ namespace eetq_b200 {
 namespace {
 
 cudaError_t launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 grid, dim3 block, size_t smem, bool pdl,
-                       cudaStream_t stream)
+                       cudaStream_t stream, int cluster_y = 0)
 {
     cfg                  = cudaLaunchConfig_t{};
     cfg.gridDim          = grid;
     cfg.blockDim         = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream           = stream;
-    attr[0].id           = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs            = attr;
-    cfg.numAttrs         = pdl ? 1 : 0;
+    int n                = 0;
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_y > 1) {
+        attr[n].id               = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = 1;
+        attr[n].val.clusterDim.y = unsigned(cluster_y);
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs    = attr;
+    cfg.numAttrs = unsigned(n);
     return cudaSuccess;
 }
 
-// x[h] = table[token][h]
+// x[h] = table[token][h]; plain or LL output (every rank gathers the same row into its own LL buffer)
 __global__ void __launch_bounds__(256) embed_kernel(const __half* __restrict__ table, const int64_t* __restrict__ token,
-                                                     __half* __restrict__ x, int H)
+                                                     __half* __restrict__ x, int H, LLTag ll)
 {
     pdl_launch_dependents();
     pdl_wait_prior_grids();
     const int64_t t = *token;
-    const uint4* src = reinterpret_cast<const uint4*>(table + t * H);
-    uint4* dst       = reinterpret_cast<uint4*>(x);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H / 8; i += gridDim.x * blockDim.x)
-        dst[i] = src[i];
+    if (ll.tag_base == nullptr) {
+        const uint4* src = reinterpret_cast<const uint4*>(table + t * H);
+        uint4* dst       = reinterpret_cast<uint4*>(x);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H / 8; i += gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    }
+    else {
+        const uint32_t tag     = ll_tag(ll);
+        const uint32_t* src    = reinterpret_cast<const uint32_t*>(table + t * H);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(x);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H / 2; i += gridDim.x * blockDim.x)
+            dst[i] = ll_pack(src[i], tag);
+    }
 }
 
-// y = fp16( fp16(x_f32 * rsqrt(mean(x^2) + eps)) * w )   (HF LlamaRMSNorm arithmetic), one CTA per row
-__global__ void __launch_bounds__(512) rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
-                                                       __half* __restrict__ y, int H, float eps, const unsigned* wait_flags,
-                                                       int world, const int* epoch)
+// y = fp16( fp16(x_f32 * rsqrt(mean(x^2) + eps)) * w )   (HF LlamaRMSNorm arithmetic), one CTA per row.
+// t5 != 0: the reference's generalT5LayerNorm arithmetic instead -- fp16( (x_f32 * rsqrt(..)) * w_f32 ), clamped to the fp16
+// range (layernorm.cu:25-51, clamp_inf_for_half).
+__global__ void __launch_bounds__(512) rmsnorm_kernel(const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ w,
+                                                       __half* __restrict__ y, int64_t ldy, int H, float eps, int t5)
 {
     __shared__ float red[16];
     pdl_launch_dependents();
     pdl_wait_prior_grids();
-    p2p_wait_flags(wait_flags, world, epoch);
-    const __half* xr = x + int64_t(blockIdx.x) * H;
-    __half* yr       = y + int64_t(blockIdx.x) * H;
+    const __half* xr = x + int64_t(blockIdx.x) * ldx;
+    __half* yr       = y + int64_t(blockIdx.x) * ldy;
     float ss = 0.f;
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
         const float v = __half2float(xr[i]);
@@ -66,21 +92,109 @@ __global__ void __launch_bounds__(512) rmsnorm_kernel(const __half* __restrict__
     for (int i = 0; i < (blockDim.x >> 5); ++i)
         tot += red[i];
     const float r = rsqrtf(tot / float(H) + eps);
-    for (int i = threadIdx.x; i < H; i += blockDim.x)
-        yr[i] = __hmul(__float2half_rn(__half2float(xr[i]) * r), w[i]);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        if (t5) {
+            float v = (__half2float(xr[i]) * r) * __half2float(w[i]);
+            v       = fminf(fmaxf(v, -65504.f), 65504.f);
+            yr[i]   = __float2half_rn(v);
+        }
+        else {
+            yr[i] = __hmul(__float2half_rn(__half2float(xr[i]) * r), w[i]);
+        }
+    }
+}
+
+// In-place GPT-NeoX rotary embedding of query and key, the reference's op of the same name
+// (pos_encoding_kernels.cu:12-53): one CTA per token, cos_sin_cache [max_position][rot_dim] = cos(rot/2) | sin(rot/2),
+// fp16 arithmetic exactly as written there (two rounded products, one rounded difference / sum).
+__global__ void rope_neox_kernel(const int64_t* __restrict__ positions, __half* __restrict__ query, __half* __restrict__ key,
+                                 const __half* __restrict__ cos_sin_cache, int rot_dim, int stride, int num_heads, int head_size)
+{
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();
+    const int token       = blockIdx.x;
+    const int64_t pos     = positions[token];
+    const __half* cache   = cos_sin_cache + pos * rot_dim;
+    const int embed_dim   = rot_dim / 2;
+    const int n           = num_heads * embed_dim;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int head = i / embed_dim, r = i - head * embed_dim;
+        const int64_t ix = int64_t(token) * stride + head * head_size + r;
+        const int64_t iy = ix + embed_dim;
+        const __half c = cache[r], s = cache[embed_dim + r];
+        const __half qx = query[ix], qy = query[iy];
+        query[ix] = __hsub(__hmul(qx, c), __hmul(qy, s));
+        query[iy] = __hadd(__hmul(qy, c), __hmul(qx, s));
+        const __half kx = key[ix], ky = key[iy];
+        key[ix] = __hsub(__hmul(kx, c), __hmul(ky, s));
+        key[iy] = __hadd(__hmul(ky, c), __hmul(kx, s));
+    }
+}
+
+// Prefill glue: for T tokens starting at cache position p0, rotate q in place (HF rotate_half convention, cos/sin tables
+// [max_pos][D/2]) and write rotated k and v into the head-major KV cache [heads][max_ctx][D].  qkv rows are q | k | v.
+__global__ void __launch_bounds__(128) rope_kv_write_kernel(__half* __restrict__ qkv, int64_t ld, const __half* __restrict__ cos_t,
+                                                             const __half* __restrict__ sin_t, __half* __restrict__ kcache,
+                                                             __half* __restrict__ vcache, int heads, int D, int max_ctx, int p0)
+{
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();
+    const int token = blockIdx.x, head = blockIdx.y;
+    const int H     = heads * D;
+    const int half  = D / 2;
+    __half* row     = qkv + int64_t(token) * ld;
+    const int pos   = p0 + token;
+    for (int t = threadIdx.x; t < half; t += blockDim.x) {
+        const float c = __half2float(cos_t[int64_t(pos) * half + t]), s = __half2float(sin_t[int64_t(pos) * half + t]);
+        const int a = head * D + t, b = a + half;
+        const float q0 = __half2float(row[a]), q1 = __half2float(row[b]);
+        row[a] = __hadd(__float2half_rn(q0 * c), __float2half_rn(-q1 * s));
+        row[b] = __hadd(__float2half_rn(q1 * c), __float2half_rn(q0 * s));
+        const float k0 = __half2float(row[H + a]), k1 = __half2float(row[H + b]);
+        const __half r0 = __hadd(__float2half_rn(k0 * c), __float2half_rn(-k1 * s));
+        const __half r1 = __hadd(__float2half_rn(k1 * c), __float2half_rn(k0 * s));
+        row[H + a] = r0;
+        row[H + b] = r1;
+        const int64_t crow = (int64_t(head) * max_ctx + pos) * D;
+        kcache[crow + t] = r0;
+        kcache[crow + t + half] = r1;
+        vcache[crow + t]        = row[2 * H + a];
+        vcache[crow + t + half] = row[2 * H + b];
+    }
+}
+
+// Prefill glue: act[t][i] = fp16(silu(g)) * u.  interleaved = 0: gu rows are gate[I] | up[I]; 1: (g0,u0,g1,u1,...)
+__global__ void __launch_bounds__(256) silu_mul_kernel(const __half* __restrict__ gu, int64_t ldg, __half* __restrict__ act,
+                                                        int64_t lda, int I, int interleaved)
+{
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();
+    const __half* row = gu + int64_t(blockIdx.y) * ldg;
+    __half* out       = act + int64_t(blockIdx.y) * lda;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < I; i += gridDim.x * blockDim.x) {
+        const __half g = interleaved ? row[2 * i] : row[i];
+        const __half u = interleaved ? row[2 * i + 1] : row[I + i];
+        const float gf = __half2float(g);
+        out[i]         = __hmul(__float2half_rn(gf / (1.f + __expf(-gf))), u);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fused RoPE + KV-append + split-KV decode attention + split merge, one query token, ONE launch per layer.
-//   grid = (heads, splits), 128 threads, head_dim 128.  CTA (h, s) owns the fixed cache rows [64 s, 64 s + 64): thread (rowlane = t/16,
-//   sub = t%16) holds 16-byte slices of 8 K rows and 8 V rows IN REGISTERS -- all 16 loads are issued up front (256 B in
-//   flight per thread), so the whole KV read of the layer is in flight at once and the kernel is a pure HBM stream.
-//   The CTA that owns the newest position rotates k, appends k/v to the cache and uses them from shared memory.
-//   Partials {o[128], m, l} go to scratch; the last CTA of a head (atomic ticket, self-resetting) merges them.
+// Decode attention: fused RoPE + KV append + attention for ONE query token, ONE launch per layer, no global scratch.
+//   grid = (local heads, 8), cluster (1, 8, 1), 128 threads, head_dim 128.  The 8 CTAs of a cluster share one head: CTA s
+//   streams the 64-row cache chunks s, s + 8, s + 16, ... (balanced for any position, and static -- so the first two chunks
+//   are requested BEFORE griddepcontrol.wait and before the position is even read, overlapping the tail of the q|k|v GEMV).
+//   Thread (rowlane = t / 16, sub = t % 16) holds 16-byte slices of 8 K rows and 8 V rows of a chunk in registers, two
+//   chunks in flight (512 bytes per thread).  Each 16-lane group runs its own online softmax (no block barriers inside the
+//   stream); the 8 groups are merged through shared memory, the 8 CTAs through DISTRIBUTED shared memory (one cluster barrier
+//   instead of round 1's global scratch + __threadfence + atomic ticket + serial merge).
+//   The CTA whose chunk holds the newest position rotates k, appends k / v to the cache and uses them from shared memory.
+//   Output: plain fp16 vector, or LL words pushed to every rank (head-sharded attention, see the file header).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ATT_D       = 128;
 constexpr int ATT_THREADS = 128;
-constexpr int ATT_ROWS    = 64;  // cache positions per CTA (8 per rowlane)
+constexpr int ATT_ROWS    = 64;  // cache positions per chunk (8 per rowlane)
+constexpr int ATT_SPLITS  = 8;   // CTAs per head == cluster size
 
 __device__ __forceinline__ float dot8(const uint4& kv, const float (&q)[8])
 {
@@ -100,59 +214,78 @@ __device__ __forceinline__ void axpy8(float p, const uint4& vv, float (&acc)[8])
     acc[4] = fmaf(p, c.x, acc[4]); acc[5] = fmaf(p, c.y, acc[5]); acc[6] = fmaf(p, d.x, acc[6]); acc[7] = fmaf(p, d.y, acc[7]);
 }
 
-__global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cos_t,
-                                                                  const __half* __restrict__ sin_t, const int* __restrict__ pos_p,
-                                                                  __half* __restrict__ kcache, __half* __restrict__ vcache,
-                                                                  float* __restrict__ partial, int* __restrict__ tickets,
-                                                                  __half* __restrict__ out, int H, int max_ctx, float scale,
-                                                                  const unsigned* wait_flags, int world, const int* epoch)
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank)
+{
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr));
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+struct AttnOut {
+    __half* out;       // plain output [heads_local * 128] (world == 1) or nullptr
+    LLPush push;       // LL output: every rank's attention vector, this rank's heads at element offset push.elem_off
+};
+
+__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cos_t,
+                                                                   const __half* __restrict__ sin_t, const int* __restrict__ pos_p,
+                                                                   __half* __restrict__ kcache, __half* __restrict__ vcache,
+                                                                   int H, int max_ctx, float scale, const AttnOut ao)
 {
     __shared__ float q_s[ATT_D];
     __shared__ __align__(16) __half knew[ATT_D];
     __shared__ __align__(16) __half vnew[ATT_D];
-    __shared__ float sc[ATT_ROWS];
-    __shared__ float red[ATT_THREADS / 32];
-    __shared__ float osum[8][ATT_D];
-    __shared__ int is_last_s;
+    __shared__ float grp_o[8][ATT_D];   // per 16-lane group partial numerators
+    __shared__ float grp_ml[8][2];      // per group (max, denominator)
+    __shared__ float cta_o[ATT_D];      // this CTA's merged partial: read by the whole cluster through DSMEM
+    __shared__ float cta_ml[2];
 
     const int t       = threadIdx.x;
-    const int lane    = t & 31;
-    const int warp    = t >> 5;
     const int sub     = t & 15;   // which 8-dim slice of the head
     const int rowlane = t >> 4;   // 0..7
     const int head    = blockIdx.x;
-    const int splits  = gridDim.y;
-    const int split   = blockIdx.y;
+    const int split   = int(cluster_ctarank());  // == blockIdx.y
 
     pdl_launch_dependents();
-    // Split s owns the FIXED cache rows [64 s, 64 s + 64): the loads below need neither `pos` nor anything the preceding
-    // kernel produces (rows < pos were written by earlier STEPS; rows >= pos are masked out later), so the whole KV
-    // stream of the layer is in flight before the dependency wait and overlaps the tail of the q|k|v GEMV.
-    const int p0 = split * ATT_ROWS;
-    uint4 kreg[8], vreg[8];
-    const __half* kbase = kcache + (int64_t(head) * max_ctx + p0) * ATT_D + sub * 8;
-    const __half* vbase = vcache + (int64_t(head) * max_ctx + p0) * ATT_D + sub * 8;
+    const __half* kbase = kcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
+    const __half* vbase = vcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
+    uint4 kreg[2][8], vreg[2][8];
+    auto load_chunk = [&](int buf, int chunk) {
+        const int p0 = chunk * ATT_ROWS;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int j = i * 8 + rowlane;
-        kreg[i]     = (p0 + j < max_ctx) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
-    }
+        for (int i = 0; i < 8; ++i) {
+            const int j  = p0 + i * 8 + rowlane;
+            kreg[buf][i] = (j < max_ctx) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int j = i * 8 + rowlane;
-        vreg[i]     = (p0 + j < max_ctx) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    const int pos = *pos_p;                            // written at the end of the previous step
-    const int L   = pos + 1;                           // attend to positions [0, pos]
-    const int n   = max(0, min(ATT_ROWS, L - p0));     // valid rows of this split
-    const bool owns_new = (pos >= p0) && (pos < p0 + ATT_ROWS);
+        for (int i = 0; i < 8; ++i) {
+            const int j  = p0 + i * 8 + rowlane;
+            vreg[buf][i] = (j < max_ctx) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    // Rows below the current position were written by earlier STEPS and rows above it are masked out later, so these loads
+    // need neither `pos` nor anything the preceding kernel produces.
+    load_chunk(0, split);
+    load_chunk(1, split + ATT_SPLITS);
+    const int pos = *pos_p;  // written at the end of the previous step
     float rope_c = 0.f, rope_s = 0.f;
     if (t < ATT_D / 2) {
         rope_c = __half2float(cos_t[int64_t(pos) * (ATT_D / 2) + t]);
         rope_s = __half2float(sin_t[int64_t(pos) * (ATT_D / 2) + t]);
     }
+    const int new_chunk = pos / ATT_ROWS;
+    const bool owns_new = (new_chunk % ATT_SPLITS) == split;
     pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
-    p2p_wait_flags(wait_flags, world, epoch);  // column-sharded q|k|v: every rank's slice must have landed
 
     // RoPE of q (every CTA) and of the new k (owner CTA); HF rotate_half convention evaluated in fp16
     if (t < ATT_D / 2) {
@@ -180,125 +313,375 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
     for (int d = 0; d < 8; ++d)
         qf[d] = q_s[sub * 8 + d];
 
-    // scores: 16 lanes share a row
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int j = i * 8 + rowlane;
-        uint4 kv    = kreg[i];
-        if (owns_new && j == n - 1)
-            kv = *reinterpret_cast<const uint4*>(&knew[sub * 8]);
-        float d = dot8(kv, qf);
-#pragma unroll
-        for (int o = 8; o >= 1; o >>= 1)
-            d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (sub == 0 && j < n)
-            sc[j] = d;
-    }
-    __syncthreads();
-
-    // softmax statistics of this chunk
-    float m = (t < n) ? sc[t] : -INFINITY;
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1)
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0)
-        red[warp] = m;
-    __syncthreads();
-    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    __syncthreads();
-    float e = 0.f;
-    if (t < n) {
-        e     = __expf(sc[t] - m);
-        sc[t] = e;
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1)
-        e += __shfl_xor_sync(0xffffffffu, e, o);
-    if (lane == 0)
-        red[warp] = e;
-    __syncthreads();
-    const float l = red[0] + red[1] + red[2] + red[3];
-
-    // o = sum_j p_j V_j : each thread accumulates its 8 dims over its rows, then the 8 rowlanes are summed in smem
+    // online softmax state of this 16-lane group (identical in all 16 lanes; each lane owns 8 dims of the numerator)
+    float m_run = -INFINITY, l_run = 0.f;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    auto process = [&](int buf, int chunk) {
+        const int p0 = chunk * ATT_ROWS;
+        float sc[8];
+        float cmax = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int j = i * 8 + rowlane;
-        if (j < n) {
-            uint4 vv = vreg[i];
-            if (owns_new && j == n - 1)
-                vv = *reinterpret_cast<const uint4*>(&vnew[sub * 8]);
-            axpy8(sc[j], vv, acc);
+        for (int i = 0; i < 8; ++i) {
+            const int j = p0 + i * 8 + rowlane;
+            uint4 kv    = kreg[buf][i];
+            if (j == pos)
+                kv = *reinterpret_cast<const uint4*>(&knew[sub * 8]);  // the row appended by this very launch
+            float d = dot8(kv, qf);
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1)
+                d += __shfl_xor_sync(0xffffffffu, d, o);
+            sc[i] = (j <= pos) ? d : -INFINITY;
+            cmax  = fmaxf(cmax, sc[i]);
         }
+        if (cmax == -INFINITY)
+            return;  // nothing valid for this group in this chunk (uniform inside the 16-lane group)
+        const float m_new = fmaxf(m_run, cmax);
+        const float resc  = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
+        l_run *= resc;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            acc[d] *= resc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = p0 + i * 8 + rowlane;
+            if (sc[i] != -INFINITY) {
+                const float p = __expf(sc[i] - m_new);
+                l_run += p;
+                uint4 vv = vreg[buf][i];
+                if (j == pos)
+                    vv = *reinterpret_cast<const uint4*>(&vnew[sub * 8]);
+                axpy8(p, vv, acc);
+            }
+        }
+        m_run = m_new;
+    };
+
+    int buf = 0;
+    for (int chunk = split; chunk * ATT_ROWS <= pos; chunk += ATT_SPLITS, buf ^= 1) {
+        process(buf, chunk);
+        const int nxt = chunk + 2 * ATT_SPLITS;
+        if (nxt * ATT_ROWS <= pos)
+            load_chunk(buf, nxt);
     }
+
+    // merge the 8 groups of this CTA
 #pragma unroll
     for (int d = 0; d < 8; ++d)
-        osum[rowlane][sub * 8 + d] = acc[d];
+        grp_o[rowlane][sub * 8 + d] = acc[d];
+    if (sub == 0) {
+        grp_ml[rowlane][0] = m_run;
+        grp_ml[rowlane][1] = l_run;
+    }
     __syncthreads();
-    float o = 0.f;
+    {
+        float mm = -INFINITY;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-        o += osum[r][t];
+        for (int r = 0; r < 8; ++r)
+            mm = fmaxf(mm, grp_ml[r][0]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float mr = grp_ml[r][0];
+            const float w  = (mr == -INFINITY) ? 0.f : __expf(mr - mm);
+            num = fmaf(w, grp_o[r][t], num);
+            den = fmaf(w, grp_ml[r][1], den);
+        }
+        cta_o[t] = num;
+        if (t == 0) {
+            cta_ml[0] = mm;
+            cta_ml[1] = den;
+        }
+    }
+    // merge the 8 CTAs of the head through distributed shared memory: CTA s finishes dims [16 s, 16 s + 16)
+    cluster_arrive();
+    cluster_wait();
+    if (t < 16) {
+        const int d = split * 16 + t;
+        float ms[ATT_SPLITS], ls[ATT_SPLITS], os[ATT_SPLITS];
+#pragma unroll
+        for (int r = 0; r < ATT_SPLITS; ++r) {
+            ms[r] = ld_dsmem_f32(&cta_ml[0], uint32_t(r));
+            ls[r] = ld_dsmem_f32(&cta_ml[1], uint32_t(r));
+            os[r] = ld_dsmem_f32(&cta_o[d], uint32_t(r));
+        }
+        float mm = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < ATT_SPLITS; ++r)
+            mm = fmaxf(mm, ms[r]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int r = 0; r < ATT_SPLITS; ++r) {
+            const float w = (ms[r] == -INFINITY) ? 0.f : __expf(ms[r] - mm);
+            num = fmaf(w, os[r], num);
+            den = fmaf(w, ls[r], den);
+        }
+        const __half o = __float2half_rn(num / den);
+        if (ao.out != nullptr) {
+            ao.out[head * ATT_D + d] = o;
+        }
+        else {
+            // LL: lanes pair up (even lane carries dims d, d + 1) and push one 8-byte word per rank
+            const uint32_t mine  = uint32_t(__half_as_ushort(o));
+            const uint32_t other = __shfl_down_sync(0x0000ffffu, mine, 1);
+            if ((t & 1) == 0)
+                ll_push_word(ao.push, (head * ATT_D + d) >> 1, mine | (other << 16));
+        }
+    }
+    // nobody may leave while a sibling still reads its shared memory
+    cluster_arrive();
+    cluster_wait();
+}
 
-    float* mine = partial + (int64_t(head) * splits + split) * (ATT_D + 2);
-    mine[t] = o;
-    if (t == 0) {
-        mine[ATT_D]     = (n > 0) ? m : -INFINITY;
-        mine[ATT_D + 1] = (n > 0) ? l : 0.f;
-    }
-    __threadfence();
-    __syncthreads();
-    if (t == 0) {
-        const int old = atomicAdd(tickets + head, 1);
-        const int last = (old == splits - 1) ? 1 : 0;
-        if (last)
-            tickets[head] = 0;  // self-cleaning for the next launch
-        is_last_s = last;
-    }
-    __syncthreads();
-    if (is_last_s) {
-        __threadfence();
-        const float* p = partial + int64_t(head) * splits * (ATT_D + 2);
-        // merge: split statistics first (parallel over splits, staged in smem), then each thread merges its own dim with
-        // independent loads kept in flight (a serial chain of L2 round trips here used to cost more than the KV stream)
-        float mm = -INFINITY, den = 0.f, num = 0.f;
-        for (int base = 0; base < splits; base += ATT_ROWS) {
-            const int cnt = min(ATT_ROWS, splits - base);
-            __syncthreads();
-            if (t < cnt) {
-                sc[t]         = __ldcg(p + (base + t) * (ATT_D + 2) + ATT_D);       // m_s
-                osum[0][t]    = __ldcg(p + (base + t) * (ATT_D + 2) + ATT_D + 1);   // l_s
-            }
-            __syncthreads();
-            float cm = mm;
-            for (int s2 = 0; s2 < cnt; ++s2)
-                cm = fmaxf(cm, sc[s2]);
-            const float rescale = (mm == -INFINITY) ? 0.f : __expf(mm - cm);
-            num *= rescale;
-            den *= rescale;
-            mm = cm;
-            int s2 = 0;
-            for (; s2 + 4 <= cnt; s2 += 4) {
-                float v[4];
+// ---------------------------------------------------------------------------------------------------------------
+// lm_head + greedy arg-max: logits[v] = sum_k RMSNorm(x)[k] * W[v, k] over this rank's vocabulary rows, fp16 weights
+// (the reference leaves lm_head unquantised, quantizer.py:40), fused final RMSNorm on the activation load, fp32
+// accumulation (FHFMA), block arg-max, and a self-resetting ticket so that the LAST CTA picks the winner, (multi-GPU:
+// exchanges candidates with the other ranks through LL words), writes the next token id, advances the position and
+// the step counter.  One launch replaces RMSNorm + cuBLAS GEMV + arg-max + two copies.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LM_THREADS = 256;
+constexpr int LM_R       = 4;   // vocabulary rows per register group
+constexpr int LM_MAXKI   = 4;   // hidden <= 8192
+
+struct LmArgs {
+    const __half* x;          // [H] plain, or LL words (x_ll.tag_base != nullptr)
+    LLTag x_ll;
+    const __half* norm_w;     // [H]
+    float eps;
+    const __half* w;          // [V_local][H]
+    int V_local, H, v_begin;  // this rank's first vocabulary row
+    __half* logits;           // optional [V_total]: this rank writes its slice (tests / callers that want logits)
+    float* cta_val;           // [grid] scratch
+    int* cta_idx;             // [grid]
+    unsigned* ticket;         // zero between launches
+    int64_t* token;           // out: next token id
+    int* pos;                 // += 1
+    int* step;                // += 1 (the LL tag base)
+    LLPush cand;              // multi-GPU: candidate exchange buffer (2 words per rank), world == 1: unused
+    int world, rank;
+};
+
+template <int KITERS>
+__global__ void __launch_bounds__(LM_THREADS, 2) lm_head_argmax_kernel(const LmArgs a)
+{
+    extern __shared__ float lm_partial[];  // [rows][8 warps]
+    __shared__ float red_s[8];
+    __shared__ float best_v[8];
+    __shared__ int best_i[8];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.H, nchunks = H >> 3;  // 16-byte chunks of 8 fp16 weights
+    const int row_begin = int((int64_t(blockIdx.x) * a.V_local) / gridDim.x);
+    const int row_end   = int((int64_t(blockIdx.x + 1) * a.V_local) / gridDim.x);
+    const int nrows     = row_end - row_begin;
+    const int ngroups   = (nrows + LM_R - 1) / LM_R;
+
+    pdl_launch_dependents();
+    uint4 wb[2][LM_R][KITERS];
+    auto load_group = [&](uint4 (&buf)[LM_R][KITERS], int g) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    v[u] = __ldcg(p + (base + s2 + u) * (ATT_D + 2) + t);
+        for (int r = 0; r < LM_R; ++r) {
+            const int row = row_begin + g * LM_R + r;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float ms = sc[s2 + u];
-                    const float w  = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
-                    num = fmaf(w, v[u], num);
-                    den = fmaf(w, osum[0][s2 + u], den);
-                }
-            }
-            for (; s2 < cnt; ++s2) {
-                const float ms = sc[s2];
-                const float w  = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
-                num = fmaf(w, __ldcg(p + (base + s2) * (ATT_D + 2) + t), num);
-                den = fmaf(w, osum[0][s2], den);
+            for (int i = 0; i < KITERS; ++i) {
+                const int c = tid + i * LM_THREADS;
+                buf[r][i]   = (row < row_end && c < nchunks) ? ldg_stream_128(a.w + int64_t(row) * H + int64_t(c) * 8)
+                                                             : make_uint4(0u, 0u, 0u, 0u);
             }
         }
-        out[head * ATT_D + t] = __float2half_rn(num / den);
+    };
+    if (ngroups > 0) load_group(wb[0], 0);
+    if (ngroups > 1) load_group(wb[1], 1);
+    pdl_wait_prior_grids();
+
+    // activation slice: 8 values per chunk, final RMSNorm applied in registers (HF arithmetic)
+    uint32_t xh[KITERS][4];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < KITERS; ++i) {
+        const int c = tid + i * LM_THREADS;
+        if (c < nchunks) {
+            if (a.x_ll.tag_base != nullptr)
+                ll_load_words<4>(reinterpret_cast<const unsigned long long*>(a.x) + int64_t(c) * 4, ll_tag(a.x_ll), xh[i]);
+            else {
+                const uint4 v = *reinterpret_cast<const uint4*>(a.x + int64_t(c) * 8);
+                xh[i][0] = v.x; xh[i][1] = v.y; xh[i][2] = v.z; xh[i][3] = v.w;
+            }
+        }
+        else {
+            xh[i][0] = xh[i][1] = xh[i][2] = xh[i][3] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xh[i][j]));
+            ss = fmaf(f.x, f.x, ss);
+            ss = fmaf(f.y, f.y, ss);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) red_s[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi)
+        tot += red_s[wi];
+    const float rn = rsqrtf(tot / float(H) + a.eps);
+#pragma unroll
+    for (int i = 0; i < KITERS; ++i) {
+        const int c = tid + i * LM_THREADS;
+        if (c < nchunks) {
+            const uint4 nw = *reinterpret_cast<const uint4*>(a.norm_w + int64_t(c) * 8);
+            const uint32_t nwr[4] = {nw.x, nw.y, nw.z, nw.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f  = __half22float2(*reinterpret_cast<const __half2*>(&xh[i][j]));
+                const __half2 n = __floats2half2_rn(f.x * rn, f.y * rn);
+                const __half2 o = __hmul2(n, *reinterpret_cast<const __half2*>(&nwr[j]));
+                xh[i][j]        = *reinterpret_cast<const uint32_t*>(&o);
+            }
+        }
+    }
+
+    auto compute_group = [&](uint4 (&buf)[LM_R][KITERS], int g) {
+        float acc[LM_R];
+#pragma unroll
+        for (int r = 0; r < LM_R; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < KITERS; ++i) {
+                const uint32_t wv[4] = {buf[r][i].x, buf[r][i].y, buf[r][i].z, buf[r][i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(s) : "h"(uint16_t(wv[j] & 0xffffu)), "h"(uint16_t(xh[i][j] & 0xffffu)));
+                    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(s) : "h"(uint16_t(wv[j] >> 16)), "h"(uint16_t(xh[i][j] >> 16)));
+                }
+            }
+            acc[r] = s;
+        }
+#pragma unroll
+        for (int r = 0; r < LM_R; ++r) {
+            float v = acc[r];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1)
+                v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0)
+                lm_partial[(g * LM_R + r) * 8 + warp] = v;
+        }
+    };
+    for (int g = 0; g < ngroups; g += 2) {
+        compute_group(wb[0], g);
+        if (g + 2 < ngroups) load_group(wb[0], g + 2);
+        if (g + 1 < ngroups) {
+            compute_group(wb[1], g + 1);
+            if (g + 3 < ngroups) load_group(wb[1], g + 3);
+        }
+    }
+    __syncthreads();
+
+    // logits of this CTA's rows (rounded to fp16 like the framework's matmul output) and the block arg-max
+    float bv = -INFINITY;
+    int bi   = 0x7fffffff;
+    for (int r = tid; r < nrows; r += LM_THREADS) {
+        float s = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < 8; ++wi)
+            s += lm_partial[r * 8 + wi];
+        const __half lh = __float2half_rn(s);
+        const int v     = a.v_begin + row_begin + r;
+        if (a.logits != nullptr)
+            a.logits[v] = lh;
+        const float lv = __half2float(lh);
+        if (lv > bv || (lv == bv && v < bi)) {
+            bv = lv;
+            bi = v;
+        }
+    }
+    auto better = [](float v1, int i1, float v2, int i2) { return v1 > v2 || (v1 == v2 && i1 < i2); };
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi   = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        best_v[warp] = bv;
+        best_i[warp] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int wi = 1; wi < 8; ++wi)
+            if (better(best_v[wi], best_i[wi], bv, bi)) {
+                bv = best_v[wi];
+                bi = best_i[wi];
+            }
+        a.cta_val[blockIdx.x] = bv;
+        a.cta_idx[blockIdx.x] = bi;
+        __threadfence();
+        const unsigned old = atomicAdd(a.ticket, 1u);
+        is_last            = (old == gridDim.x - 1) ? 1 : 0;
+        if (is_last)
+            *a.ticket = 0;  // self-cleaning
+    }
+    __syncthreads();
+    if (!is_last)
+        return;
+    // last CTA: winner over all CTAs of this rank (first maximum, like torch.argmax)
+    __threadfence();
+    bv = -INFINITY;
+    bi = 0x7fffffff;
+    for (int c = tid; c < int(gridDim.x); c += LM_THREADS) {
+        const float v = __ldcg(a.cta_val + c);
+        const int i   = __ldcg(a.cta_idx + c);
+        if (better(v, i, bv, bi)) {
+            bv = v;
+            bi = i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi   = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        best_v[warp] = bv;
+        best_i[warp] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int wi = 1; wi < 8; ++wi)
+            if (better(best_v[wi], best_i[wi], bv, bi)) {
+                bv = best_v[wi];
+                bi = best_i[wi];
+            }
+        if (a.world > 1) {
+            // publish this rank's candidate to every rank (words 2 r and 2 r + 1 of the candidate buffer), then gather
+            const uint32_t tag = ll_tag(a.cand.tag);
+            ll_push_word(a.cand, 2 * a.rank, __float_as_uint(bv));
+            ll_push_word(a.cand, 2 * a.rank + 1, uint32_t(bi));
+            const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(a.cand.local);
+            for (int r = 0; r < a.world; ++r) {
+                uint32_t w2[2];
+                ll_load_words<2>(mine + 2 * r, tag, w2);
+                const float v = __uint_as_float(w2[0]);
+                const int i   = int(w2[1]);
+                if (better(v, i, bv, bi)) {
+                    bv = v;
+                    bi = i;
+                }
+            }
+        }
+        *a.token = int64_t(bi);
+        *a.pos += 1;
+        *a.step += 1;
     }
 }
 
@@ -307,166 +690,207 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fused_kernel(const __half* _
 
 using namespace eetq_b200;
 
+namespace {
+int fill_push(LLPush& p, int world, const uint64_t* peers, void* local, int64_t elem_off, const void* step, int per_step, int index)
+{
+    p = LLPush{};
+    p.world = world;
+    for (int r = 0; r < world && r < 8; ++r)
+        p.peer[r] = peers[r];
+    p.local       = static_cast<unsigned long long*>(local);
+    p.elem_off    = int(elem_off);
+    p.tag.tag_base = static_cast<const int*>(step);
+    p.tag.per_step = per_step;
+    p.tag.index    = index;
+    return EETQ_B200_OK;
+}
+}  // namespace
+
 extern "C" {
 
-int eetq_b200_decode_rmsnorm_p2p(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, const void* wait_flags,
-                                 int world, const void* epoch, int pdl, void* stream);
-int eetq_b200_decode_attention_p2p(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
-                                   void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
-                                   const void* wait_flags, int world, const void* epoch, int pdl, void* stream);
-
-int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, int pdl, void* stream)
+int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, const eetq_b200_ll* x_ll, int pdl, void* stream)
 {
     EB_CHECK_ARG(table && token_i64 && x && H % 8 == 0, "decode_embed: bad argument");
+    LLTag tag{};
+    if (x_ll != nullptr && x_ll->step != nullptr) {
+        tag.tag_base = static_cast<const int*>(x_ll->step);
+        tag.per_step = x_ll->per_step;
+        tag.index    = x_ll->index;
+    }
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     launch_cfg(cfg, attr, dim3(unsigned((H / 8 + 255) / 256)), dim3(256), 0, pdl != 0, static_cast<cudaStream_t>(stream));
     EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, embed_kernel, static_cast<const __half*>(table), static_cast<const int64_t*>(token_i64),
-                                     static_cast<__half*>(x), int(H)));
+                                     static_cast<__half*>(x), int(H), tag));
     count_launch();
     return EETQ_B200_OK;
 }
 
-int eetq_b200_decode_rmsnorm(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, int pdl, void* stream)
+int eetq_b200_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int64_t M, int64_t H, float eps, int pdl, void* stream)
 {
-    return eetq_b200_decode_rmsnorm_p2p(x, w, y, M, H, eps, nullptr, 1, nullptr, pdl, stream);
-}
-
-int eetq_b200_decode_rmsnorm_p2p(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, const void* wait_flags,
-                                 int world, const void* epoch, int pdl, void* stream)
-{
-    EB_CHECK_ARG(x && w && y && M > 0 && H > 0, "decode_rmsnorm: bad argument");
+    EB_CHECK_ARG(x && w && y && M > 0 && H > 0 && ldx >= H && ldy >= H, "rmsnorm: bad argument");
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     launch_cfg(cfg, attr, dim3(unsigned(M)), dim3(512), 0, pdl != 0, static_cast<cudaStream_t>(stream));
-    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rmsnorm_kernel, static_cast<const __half*>(x), static_cast<const __half*>(w),
-                                     static_cast<__half*>(y), int(H), eps, static_cast<const unsigned*>(wait_flags), world,
-                                     static_cast<const int*>(epoch)));
+    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rmsnorm_kernel, static_cast<const __half*>(x), ldx, static_cast<const __half*>(w),
+                                     static_cast<__half*>(y), ldy, int(H), eps, 0));
     count_launch();
     return EETQ_B200_OK;
 }
 
-// Number of KV splits the fused attention kernel needs for a cache of max_ctx positions (<= 64 positions per CTA).
-int64_t eetq_b200_decode_attention_splits(int64_t max_ctx) { return (max_ctx + ATT_ROWS - 1) / ATT_ROWS; }
+// layernorm_forward of the reference (csrc/eetpy.cpp:19 -> layernorm.cu:88-110): fp16 [m, n] rows, T5-style RMS norm
+int eetq_b200_layernorm_forward(const void* input, const void* gamma, void* out, int64_t m, int64_t n, float eps, void* stream)
+{
+    EB_CHECK_ARG(input && gamma && out && m > 0 && n > 0, "layernorm_forward: bad argument");
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    launch_cfg(cfg, attr, dim3(unsigned(m)), dim3(512), 0, false, static_cast<cudaStream_t>(stream));
+    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rmsnorm_kernel, static_cast<const __half*>(input), n, static_cast<const __half*>(gamma),
+                                     static_cast<__half*>(out), n, int(n), eps, 1));
+    count_launch();
+    return EETQ_B200_OK;
+}
 
-// Fused RoPE + KV append + attention for one token at position *pos (reads [0, pos], writes cache row pos).
-//   qkv [3H] raw projections (not modified); kcache/vcache [H/D][max_ctx][D] (head-major); partial: (H/D) * splits * 130 floats scratch; tickets: H/D ints, ZERO on
-//   first use (the kernel leaves them zero); out [H].
+// rotary_embedding_neox of the reference (csrc/eetpy.cpp:18 -> pos_encoding_kernels.cu:55-87): in place on query and key
+int eetq_b200_rotary_embedding_neox(const void* positions_i64, void* query, void* key, int64_t num_tokens, int64_t num_heads,
+                                    int64_t head_size, const void* cos_sin_cache, int64_t rot_dim, void* stream)
+{
+    EB_CHECK_ARG(positions_i64 && query && key && cos_sin_cache, "rotary_embedding_neox: null pointer argument");
+    EB_CHECK_ARG(num_tokens > 0 && num_heads > 0 && head_size > 0 && rot_dim > 0 && rot_dim % 2 == 0 && rot_dim <= head_size,
+                 "rotary_embedding_neox: bad shape");
+    const int threads = int(num_heads * rot_dim / 2 < 512 ? num_heads * rot_dim / 2 : 512);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    launch_cfg(cfg, attr, dim3(unsigned(num_tokens)), dim3(unsigned(threads < 32 ? 32 : threads)), 0, false, static_cast<cudaStream_t>(stream));
+    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rope_neox_kernel, static_cast<const int64_t*>(positions_i64), static_cast<__half*>(query),
+                                     static_cast<__half*>(key), static_cast<const __half*>(cos_sin_cache), int(rot_dim),
+                                     int(num_heads * head_size), int(num_heads), int(head_size)));
+    count_launch();
+    return EETQ_B200_OK;
+}
+
+int eetq_b200_prefill_rope_kv(void* qkv, int64_t ld, const void* cos_t, const void* sin_t, void* kcache, void* vcache, int64_t T,
+                              int64_t heads, int64_t D, int64_t max_ctx, int64_t p0, void* stream)
+{
+    EB_CHECK_ARG(qkv && cos_t && sin_t && kcache && vcache && T > 0 && heads > 0 && D > 0 && D % 2 == 0, "prefill_rope_kv: bad argument");
+    EB_CHECK_ARG(p0 >= 0 && p0 + T <= max_ctx && ld >= 3 * heads * D, "prefill_rope_kv: positions exceed the cache or bad stride");
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    launch_cfg(cfg, attr, dim3(unsigned(T), unsigned(heads)), dim3(128), 0, false, static_cast<cudaStream_t>(stream));
+    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rope_kv_write_kernel, static_cast<__half*>(qkv), ld, static_cast<const __half*>(cos_t),
+                                     static_cast<const __half*>(sin_t), static_cast<__half*>(kcache), static_cast<__half*>(vcache),
+                                     int(heads), int(D), int(max_ctx), int(p0)));
+    count_launch();
+    return EETQ_B200_OK;
+}
+
+int eetq_b200_silu_mul(const void* gu, int64_t ldg, void* act, int64_t lda, int64_t T, int64_t I, int interleaved, void* stream)
+{
+    EB_CHECK_ARG(gu && act && T > 0 && I > 0 && ldg >= 2 * I && lda >= I, "silu_mul: bad argument");
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    launch_cfg(cfg, attr, dim3(unsigned((I + 255) / 256), unsigned(T)), dim3(256), 0, false, static_cast<cudaStream_t>(stream));
+    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, silu_mul_kernel, static_cast<const __half*>(gu), ldg, static_cast<__half*>(act), lda, int(I),
+                                     interleaved));
+    count_launch();
+    return EETQ_B200_OK;
+}
+
+// Fused RoPE + KV append + attention for one token at position *pos (reads rows [0, pos], writes cache row pos).
+//   qkv [3 * H_local] raw projections of this rank's heads (q | k | v, not modified); kcache/vcache [H_local/D][max_ctx][D]
+//   (head-major); out [H_local] plain fp16, or NULL with `push` describing the LL exchange of the full attention vector.
 int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
-                               void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
+                               void* vcache, void* out, int64_t H_local, int64_t D, int64_t max_ctx, const eetq_b200_ll_push* push,
                                int pdl, void* stream)
 {
-    return eetq_b200_decode_attention_p2p(qkv, cos_t, sin_t, pos_i32, kcache, vcache, partial, tickets, out, H, D, max_ctx, nullptr, 1,
-                                          nullptr, pdl, stream);
-}
-
-int eetq_b200_decode_attention_p2p(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
-                                   void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
-                                   const void* wait_flags, int world, const void* epoch, int pdl, void* stream)
-{
-    EB_CHECK_ARG(qkv && cos_t && sin_t && pos_i32 && kcache && vcache && partial && tickets && out,
-                 "decode_attention: null pointer argument");
-    EB_CHECK_ARG(D == ATT_D && H % D == 0, "decode_attention: head_dim must be 128");
+    EB_CHECK_ARG(qkv && cos_t && sin_t && pos_i32 && kcache && vcache, "decode_attention: null pointer argument");
+    EB_CHECK_ARG((out != nullptr) != (push != nullptr), "decode_attention: exactly one of out / push must be given");
+    EB_CHECK_ARG(D == ATT_D && H_local % D == 0 && H_local > 0, "decode_attention: head_dim must be 128");
     EB_CHECK_ARG(max_ctx >= 1 && max_ctx <= (1 << 20), "decode_attention: bad max_ctx");
-    const int heads  = int(H / D);
-    const int splits = int(eetq_b200_decode_attention_splits(max_ctx));
+    AttnOut ao{};
+    ao.out = static_cast<__half*>(out);
+    if (push != nullptr) {
+        EB_CHECK_ARG(push->world >= 1 && push->world <= 8 && push->step != nullptr && push->peers != nullptr, "decode_attention: bad LL push");
+        fill_push(ao.push, push->world, push->peers, push->local, push->elem_off, push->step, push->per_step, push->index);
+    }
+    const int heads = int(H_local / D);
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
-    launch_cfg(cfg, attr, dim3(unsigned(heads), unsigned(splits)), dim3(ATT_THREADS), 0, pdl != 0, static_cast<cudaStream_t>(stream));
-    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_fused_kernel, static_cast<const __half*>(qkv), static_cast<const __half*>(cos_t),
+    cudaLaunchAttribute attr[2];
+    launch_cfg(cfg, attr, dim3(unsigned(heads), ATT_SPLITS), dim3(ATT_THREADS), 0, pdl != 0, static_cast<cudaStream_t>(stream), ATT_SPLITS);
+    EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel, static_cast<const __half*>(qkv), static_cast<const __half*>(cos_t),
                                      static_cast<const __half*>(sin_t), static_cast<const int*>(pos_i32), static_cast<__half*>(kcache),
-                                     static_cast<__half*>(vcache), static_cast<float*>(partial), static_cast<int*>(tickets),
-                                     static_cast<__half*>(out), int(H), int(max_ctx), 1.0f / sqrtf(float(D)),
-                                     static_cast<const unsigned*>(wait_flags), world, static_cast<const int*>(epoch)));
+                                     static_cast<__half*>(vcache), int(H_local), int(max_ctx), 1.0f / sqrtf(float(D)), ao));
     count_launch();
     return EETQ_B200_OK;
 }
 
-// The decode GEMV with its fusions exposed: optional RMSNorm / SiLU*up on the activation load, optional residual add.
-//   xmode: 0 plain, 1 RMSNorm(x; norm_weight, eps), 2 silu(x[:, :K]) * x[:, K:2K]
-int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
-                               const void* norm_weight, float eps, int xmode, const void* residual, int64_t ldr, void* y,
-                               int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, int pdl, void* stream)
+size_t eetq_b200_lm_head_scratch_bytes(void)
 {
-    EB_CHECK_ARG(x && w_b200 && scales && y, "w8a16_gemv_fused: null pointer argument");
-    EB_CHECK_ARG(M >= 1 && M <= EETQ_B200_GEMV_MAX_M, "w8a16_gemv_fused: M must be in [1, %d]", EETQ_B200_GEMV_MAX_M);
-    EB_CHECK_ARG(K > 0 && N > 0 && K % 64 == 0 && N % 64 == 0, "w8a16_gemv_fused: K and N must be positive multiples of 64");
-    EB_CHECK_ARG(xmode >= 0 && xmode <= 2 && (xmode != GEMV_X_RMSNORM || norm_weight != nullptr), "w8a16_gemv_fused: bad xmode");
-    EB_CHECK_ARG(ldx >= (xmode == GEMV_X_SILU_MUL ? 2 * K : K) && ldy >= N, "w8a16_gemv_fused: bad leading dimension");
-    GemvExtras ex;
-    ex.norm_weight = norm_weight;
-    ex.residual    = residual;
-    ex.ldr         = ldr;
-    ex.eps         = eps;
-    ex.xmode       = xmode;
-    return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl != 0, static_cast<cudaStream_t>(stream));
+    const DeviceInfo& di = device_info();
+    const int grid       = (di.ok ? di.sm_count : 148) * 2;
+    return size_t(grid) * 8 + 64;
 }
 
-
-// eetq_b200_w8a16_gemv_fused + an L2 prefetch of the KV cache rows [0, *pos) (layout [heads][max_ctx][128] fp16) that the
-// attention kernel launched right after it will read: issued by the GEMV CTAs once their weight stream is in flight.
-int eetq_b200_w8a16_gemv_fused_kvprefetch(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
-                                          float eps, int xmode, const void* residual, int64_t ldr, void* y, int64_t ldy, int64_t M,
-                                          int64_t N, int64_t K, int dtype, const void* kcache, const void* vcache, const void* pos_i32,
-                                          int64_t heads, int64_t max_ctx, int pdl, void* stream)
+// logits = RMSNorm(x; norm_w, eps) @ W^T over V_local rows, arg-max -> *token; *pos += 1; *step += 1.
+//   scratch: eetq_b200_lm_head_scratch_bytes() bytes, ZERO on first use (left clean).  x_ll / cand: NULL on one GPU.
+int eetq_b200_lm_head_argmax(const void* x, const eetq_b200_ll* x_ll, const void* norm_w, float eps, const void* w, int64_t V_local,
+                             int64_t H, int64_t v_begin, void* logits, void* scratch, void* token_i64, void* pos_i32, void* step_i32,
+                             const eetq_b200_ll_push* cand, int rank, int pdl, void* stream)
 {
-    EB_CHECK_ARG(x && w_b200 && scales && y && kcache && vcache && pos_i32, "w8a16_gemv_fused_kvprefetch: null pointer argument");
-    EB_CHECK_ARG(M >= 1 && M <= EETQ_B200_GEMV_MAX_M && K > 0 && N > 0 && K % 64 == 0 && N % 64 == 0, "w8a16_gemv_fused_kvprefetch: bad shape");
-    GemvExtras ex;
-    ex.norm_weight = norm_weight;
-    ex.residual    = residual;
-    ex.ldr         = ldr;
-    ex.eps         = eps;
-    ex.xmode       = xmode;
-    ex.pf_k        = kcache;
-    ex.pf_v        = vcache;
-    ex.pf_pos      = static_cast<const int*>(pos_i32);
-    ex.pf_heads    = int(heads);
-    ex.pf_max_ctx  = int(max_ctx);
-    return launch_gemv(x, ldx, w_b200, scales, nullptr, y, ldy, int(M), N, K, dtype, ex, pdl != 0, static_cast<cudaStream_t>(stream));
-}
-
-// Up to 4 dependent M=1 fp16 GEMVs in one launch (see w8a16_gemv_chain_kernel).  `phases` is an array of
-// eetq_b200_gemv_phase (layout-identical to eetq_b200::GemvChainPhase); counters: >= nphases-1 uint32, zero on first use,
-// PRIVATE to this chain position (they only ever increase); epoch: device int32 >= 1 that increases by 1 per launch.
-int eetq_b200_w8a16_gemv_chain(const void* phases, int nphases, void* counters, const void* epoch, int pdl, void* stream)
-{
-    EB_CHECK_ARG(phases && counters && epoch, "w8a16_gemv_chain: null pointer argument");
-    return launch_gemv_chain(static_cast<const GemvChainPhase*>(phases), nphases, static_cast<unsigned*>(counters),
-                             static_cast<const int*>(epoch), pdl != 0, static_cast<cudaStream_t>(stream));
-}
-
-// Column-sharded variant with the all-gather fused into the epilogue over NVLink peer memory (see GemvP2P in common.cuh).
-//   peer_y[r]    : rank r's copy of the FULL output vector, offset to this rank's first row (device-mapped peer pointer)
-//   peer_flag[r] : address on rank r of flags[slot][this rank];  local_flags: this rank's flags[slot][0..world)
-//   ticket       : local uint32, zero between calls;  epoch: device int32 that strictly increases every decode step
-int eetq_b200_w8a16_gemv_fused_p2p(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
-                                   float eps, int xmode, const void* residual, int64_t ldr, int64_t M, int64_t N_local, int64_t K,
-                                   int dtype, int world, const uint64_t* peer_y, const uint64_t* peer_flag, const void* local_flags,
-                                   const void* wait_flags, void* ticket, const void* epoch, int64_t ldy, int pdl, void* stream)
-{
-    EB_CHECK_ARG(x && w_b200 && scales && peer_y && peer_flag && local_flags && ticket && epoch, "gemv_fused_p2p: null pointer argument");
-    EB_CHECK_ARG(world >= 2 && world <= 8, "gemv_fused_p2p: world must be in [2, 8]");
-    EB_CHECK_ARG(M >= 1 && M <= EETQ_B200_GEMV_MAX_M, "gemv_fused_p2p: M must be in [1, %d]", EETQ_B200_GEMV_MAX_M);
-    EB_CHECK_ARG(K > 0 && N_local > 0 && K % 64 == 0 && N_local % 64 == 0, "gemv_fused_p2p: K and N_local must be positive multiples of 64");
-    GemvExtras ex;
-    ex.norm_weight = norm_weight;
-    ex.residual    = residual;
-    ex.ldr         = ldr;
-    ex.eps         = eps;
-    ex.xmode       = xmode;
-    ex.p2p.world   = world;
-    for (int r = 0; r < world; ++r) {
-        ex.p2p.peer_y[r]    = peer_y[r];
-        ex.p2p.peer_flag[r] = peer_flag[r];
+    EB_CHECK_ARG(x && norm_w && w && scratch && token_i64 && pos_i32 && step_i32, "lm_head_argmax: null pointer argument");
+    EB_CHECK_ARG(V_local > 0 && H > 0 && H % 8 == 0 && H <= LM_MAXKI * LM_THREADS * 8, "lm_head_argmax: bad shape (hidden <= %d)",
+                 LM_MAXKI * LM_THREADS * 8);
+    const DeviceInfo& di = device_info();
+    EB_CHECK_ARG(di.ok, "lm_head_argmax: device query failed");
+    int grid = di.sm_count * 2;
+    if (grid > V_local) grid = int(V_local);
+    LmArgs a{};
+    a.x = static_cast<const __half*>(x);
+    if (x_ll != nullptr && x_ll->step != nullptr) {
+        a.x_ll.tag_base = static_cast<const int*>(x_ll->step);
+        a.x_ll.per_step = x_ll->per_step;
+        a.x_ll.index    = x_ll->index;
     }
-    ex.p2p.local_flags = static_cast<const unsigned*>(local_flags);
-    ex.p2p.wait_flags  = static_cast<const unsigned*>(wait_flags);
-    ex.p2p.ticket      = static_cast<unsigned*>(ticket);
-    ex.p2p.epoch       = static_cast<const int*>(epoch);
-    void* y_self       = reinterpret_cast<void*>(peer_y[0]);  // unused in p2p mode (stores go through peer_y)
-    return launch_gemv(x, ldx, w_b200, scales, nullptr, y_self, ldy, int(M), N_local, K, dtype, ex, pdl != 0,
-                       static_cast<cudaStream_t>(stream));
+    a.norm_w  = static_cast<const __half*>(norm_w);
+    a.eps     = eps;
+    a.w       = static_cast<const __half*>(w);
+    a.V_local = int(V_local);
+    a.H       = int(H);
+    a.v_begin = int(v_begin);
+    a.logits  = static_cast<__half*>(logits);
+    uint8_t* s = static_cast<uint8_t*>(scratch);
+    a.ticket  = reinterpret_cast<unsigned*>(s);
+    a.cta_val = reinterpret_cast<float*>(s + 64);
+    a.cta_idx = reinterpret_cast<int*>(s + 64 + size_t(di.sm_count) * 2 * 4);
+    a.token   = static_cast<int64_t*>(token_i64);
+    a.pos     = static_cast<int*>(pos_i32);
+    a.step    = static_cast<int*>(step_i32);
+    a.world   = 1;
+    a.rank    = rank;
+    if (cand != nullptr && cand->world > 1) {
+        EB_CHECK_ARG(cand->world <= 8 && cand->step != nullptr && cand->peers != nullptr && cand->local != nullptr, "lm_head_argmax: bad LL push");
+        fill_push(a.cand, cand->world, cand->peers, cand->local, 0, cand->step, cand->per_step, cand->index);
+        a.world = cand->world;
+    }
+    const int max_rows  = int((V_local + grid - 1) / grid);
+    const size_t smem   = size_t((max_rows + LM_R - 1) / LM_R * LM_R) * 8 * sizeof(float);
+    const int kiters    = int((H / 8 + LM_THREADS - 1) / LM_THREADS);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    launch_cfg(cfg, attr, dim3(unsigned(grid)), dim3(LM_THREADS), smem, pdl != 0, static_cast<cudaStream_t>(stream));
+    cudaError_t e;
+    switch (kiters) {
+        case 1: e = cudaLaunchKernelEx(&cfg, lm_head_argmax_kernel<1>, a); break;
+        case 2: e = cudaLaunchKernelEx(&cfg, lm_head_argmax_kernel<2>, a); break;
+        case 3: e = cudaLaunchKernelEx(&cfg, lm_head_argmax_kernel<3>, a); break;
+        default: e = cudaLaunchKernelEx(&cfg, lm_head_argmax_kernel<4>, a); break;
+    }
+    count_launch();
+    if (e != cudaSuccess) {
+        set_error("lm_head_argmax launch failed: %s", cudaGetErrorString(e));
+        return EETQ_B200_ECUDA;
+    }
+    return EETQ_B200_OK;
 }
 
 }  // extern "C"

@@ -175,7 +175,33 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// one elected lane of a fully converged warp (the whole warp runs the surrounding loop, so every value that feeds the
+// tcgen05 / TMA instructions stays provably warp-uniform and lives in uniform registers; round 1 ran these loops under
+// `if (lane == 0)`, which made the compiler wrap EVERY tcgen05.mma / commit / TMA in a per-instruction "which lanes hold which
+// value" loop -- ~120 cycles per issue, the 0.39 us per 64-k block floor of the round-1 kernel)
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void joint_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(THREADS) : "memory"); }
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
 {
     int v;
@@ -257,21 +283,21 @@ struct TcParams {
     int M, N, K;
     int n_tiles, t_tiles;
     int spt;           // 256-k stages per tile
-    int total_units;   // tiles * spt
+    int units_q, units_r;  // CTA g owns units [g q + min(g, r), ...): the first r CTAs take q + 1 (tile-aligned mode: tiles)
     int tile_aligned;  // 1: every CTA owns whole tiles (no workspace needed)
     int* flags;        // [grid] zero on entry, zero on exit
     float* slots;      // [grid][BT][128] fp32 partial tiles
     unsigned long long* trace;  // optional [grid][TRACE_SLOTS] clock samples (instrumented build only)
 };
 
-__device__ __forceinline__ int unit_begin(const TcParams& p, int g, int G)
+__device__ __forceinline__ int unit_begin(const TcParams& p, int g)
 {
-    if (p.tile_aligned) {
-        const int tiles = p.n_tiles * p.t_tiles;
-        return int((int64_t(g) * tiles) / G) * p.spt;
-    }
-    return int((int64_t(g) * p.total_units) / G);
+    const int b = g * p.units_q + min(g, p.units_r);
+    return p.tile_aligned ? b * p.spt : b;
 }
+// partial-tile slot layout: [BT / 4][128 rows][4 columns] fp32 -- a thread's 4 consecutive columns are one 16-byte access and
+// a warp's accesses are contiguous
+__device__ __forceinline__ int slot_index(int c, int row) { return ((c >> 2) * BLOCK_N + row) * 4; }
 
 __device__ __forceinline__ unsigned long long clk64()
 {
@@ -287,6 +313,118 @@ __device__ __forceinline__ unsigned long long gtime_ns()
 }
 
 // ------------------------------------------------------------------------------------------------- kernel
+struct Segment {
+    int tile, s0, s1, n_tile, t_tile;
+};
+__device__ __forceinline__ Segment segment_at(const TcParams& p, int u, int u1)
+{
+    Segment sg;
+    sg.tile   = u / p.spt;
+    sg.s0     = u - sg.tile * p.spt;
+    sg.s1     = min(p.spt, sg.s0 + (u1 - u));
+    sg.t_tile = sg.tile / p.n_tiles;
+    sg.n_tile = sg.tile - sg.t_tile * p.n_tiles;
+    return sg;
+}
+
+// Epilogue of one segment for the columns {16 (part + i nparts)} of accumulator buffer d, by the calling warp (TMEM lane
+// quadrant `quad`).  kind 0: whole tile -> y;  1: contributor -> workspace slot;  2: owner -> own accumulator + the slots of
+// CTAs g+1 .. g_last, in that (= ascending k) order -> y.
+template <typename T, int BT, bool SCALE_IN_A, int FB>
+__device__ __forceinline__ void epilogue_columns(const TcParams& p, const Segment& sg, int kind, uint32_t tmem_d, int quad, int lane,
+                                                 int part, int nparts, int g, int g_last, uint32_t tempty_bar_or_0)
+{
+    const int row   = quad * 32 + lane;
+    const int n     = sg.n_tile * BLOCK_N + row;
+    const bool n_ok = n < p.N;
+    float scale_f = 1.f, bias_f = 0.f;
+    if (kind != 1 && n_ok) {
+        if constexpr (!SCALE_IN_A)
+            scale_f = to_float(static_cast<const T*>(p.scales)[n]);
+        if (p.bias != nullptr)
+            bias_f = to_float(static_cast<const T*>(p.bias)[n]);
+    }
+    T* y           = static_cast<T*>(p.y);
+    float* my_slot = p.slots + size_t(g) * (BT * BLOCK_N);
+    constexpr int NCHUNK = BT / 16;
+#pragma unroll 1
+    for (int ci = part; ci < NCHUNK; ci += nparts) {
+        const int c0 = ci * 16;
+        // owner: request the contributors' partials for this chunk first (independent loads, FB contributors per batch in
+        // flight), then read the own accumulator while they travel
+        float4 w[FB][4];
+        int gg0 = g + 1;
+        if (kind == 2) {
+#pragma unroll
+            for (int b = 0; b < FB; ++b)
+                if (gg0 + b <= g_last) {
+                    const float4* src = reinterpret_cast<const float4*>(p.slots + size_t(gg0 + b) * (BT * BLOCK_N) + slot_index(c0, row));
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        w[b][q4] = __ldcg(src + q4 * BLOCK_N);
+                }
+        }
+        uint32_t r[16];
+        tmem_ld_x16(tmem_d + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
+        tmem_ld_wait();
+        if (tempty_bar_or_0 != 0 && ci + nparts >= NCHUNK) {
+            // all of this accumulator is in registers: let the MMA issuer reuse it for the next segment
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(tempty_bar_or_0);
+        }
+        if (kind == 1) {
+            float4* dst = reinterpret_cast<float4*>(my_slot + slot_index(c0, row));
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+                dst[q4 * BLOCK_N] = make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]), __uint_as_float(r[4 * q4 + 2]),
+                                                __uint_as_float(r[4 * q4 + 3]));
+            continue;
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            v[j] = __uint_as_float(r[j]);
+        if (kind == 2) {
+            while (true) {
+#pragma unroll
+                for (int b = 0; b < FB; ++b)
+                    if (gg0 + b <= g_last) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            v[4 * q4] += w[b][q4].x;
+                            v[4 * q4 + 1] += w[b][q4].y;
+                            v[4 * q4 + 2] += w[b][q4].z;
+                            v[4 * q4 + 3] += w[b][q4].w;
+                        }
+                    }
+                gg0 += FB;
+                if (gg0 > g_last)
+                    break;
+#pragma unroll
+                for (int b = 0; b < FB; ++b)
+                    if (gg0 + b <= g_last) {
+                        const float4* src = reinterpret_cast<const float4*>(p.slots + size_t(gg0 + b) * (BT * BLOCK_N) + slot_index(c0, row));
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            w[b][q4] = __ldcg(src + q4 * BLOCK_N);
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int t = sg.t_tile * BT + c0 + j;
+            if (n_ok && t < p.M) {
+                T o = from_float<T>(v[j] * scale_f + bias_f);
+                if (p.residual != nullptr)
+                    o = from_float<T>(to_float(o) + to_float(static_cast<const T*>(p.residual)[int64_t(t) * p.ldr + n]));
+                y[int64_t(t) * p.ldy + n] = o;
+            }
+        }
+    }
+}
+
 template <typename T, int BT, int DQW, bool TRACE>
 __global__ void __launch_bounds__(tc_threads(DQW), 1)
     w8a16_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p)
@@ -305,6 +443,7 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
     constexpr int W_PRODUCER_WARP = EPI_WARPS + DQW;
     constexpr int MMA_WARP        = EPI_WARPS + DQW + 1;
     constexpr int X_PRODUCER_WARP = EPI_WARPS + DQW + 2;
+    constexpr int JOINT_THREADS   = (EPI_WARPS + DQW) * 32;  // epilogue + dequant warps: together they finish an owned tile
     static_assert(DQW == 8 || DQW == 16, "8 or 16 dequant warps");
     static_assert(ND * BT <= A_COL0, "accumulators must fit below the A ring");
 
@@ -324,12 +463,12 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
     const uint32_t tmem_holder = tempty_bar + 2 * 8;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to smem_base
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = int(warp_uniform(threadIdx.x >> 5));
     const int lane = threadIdx.x & 31;
     const int g    = blockIdx.x;
     const int G    = gridDim.x;
-    const int u0   = unit_begin(p, g, G);
-    const int u1   = unit_begin(p, g + 1, G);
+    const int u0   = unit_begin(p, g);
+    const int u1   = unit_begin(p, g + 1);
 
     unsigned long long* tr = nullptr;
     if constexpr (TRACE) {
@@ -367,7 +506,7 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_holder - smem_base));
+    const uint32_t tmem_base = warp_uniform(*reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_holder - smem_base)));
 
     pdl_launch_dependents();
     if constexpr (TRACE) {
@@ -375,84 +514,92 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
             tr[50] = clk64();
     }
 
+    // The last segment of a CTA's range may be an OWNED tile whose remaining k range was computed by the following CTAs:
+    // its epilogue (own accumulator + their partials) is done by the epilogue AND dequant warps together at the very end.
+    bool last_is_fixup = false;
+    {
+        // walk to the last segment (at most a handful of iterations)
+        int u = u0;
+        Segment sg{};
+        while (u < u1) {
+            sg = segment_at(p, u, u1);
+            u += sg.s1 - sg.s0;
+        }
+        last_is_fixup = (u1 > u0) && sg.s0 == 0 && sg.s1 < p.spt;
+    }
+
     if (warp == W_PRODUCER_WARP) {
-        // ============================================================== weight TMA producer
+        // ============================================================== weight TMA producer (whole warp loops, one lane issues)
         // Weights never depend on the previous kernel in the stream: no griddepcontrol.wait here, the stream starts at once
-        if (lane == 0) {
-            int wcount = 0;
-            for (int u = u0; u < u1;) {
-                const int tile   = u / p.spt;
-                const int s0     = u - tile * p.spt;
-                const int s1     = min(p.spt, s0 + (u1 - u));
-                const int n_tile = tile % p.n_tiles;
-                for (int st = s0; st < s1; ++st, ++wcount) {
-                    const int ws       = wcount % WS;
-                    const uint32_t wph = (wcount / WS) & 1;
-                    mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
+        int wcount = 0;
+        for (int u = u0; u < u1;) {
+            const Segment sg = segment_at(p, u, u1);
+            for (int st = sg.s0; st < sg.s1; ++st, ++wcount) {
+                const int ws       = wcount % WS;
+                const uint32_t wph = (wcount / WS) & 1;
+                mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
+                if (elect_one_sync()) {
                     mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
                     // k beyond K (last stage when K % 256 != 0) is zero-filled by TMA; the matching activations are
                     // zero-filled too, so those products vanish
-                    tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, st * STAGE_K, n_tile * BLOCK_N);
-                    tma_load_2d(w8_base + ws * W_STAGE + W_BOX_BYTES, &map_w, wfull_bar + 8 * ws, st * STAGE_K + 128, n_tile * BLOCK_N);
-                    if constexpr (TRACE) {
-                        if (wcount == 0) tr[51] = clk64();
-                    }
+                    tma_load_2d(w8_base + ws * W_STAGE, &map_w, wfull_bar + 8 * ws, st * STAGE_K, sg.n_tile * BLOCK_N);
+                    tma_load_2d(w8_base + ws * W_STAGE + W_BOX_BYTES, &map_w, wfull_bar + 8 * ws, st * STAGE_K + 128, sg.n_tile * BLOCK_N);
                 }
-                u += s1 - s0;
+                __syncwarp();
+                if constexpr (TRACE) {
+                    if (wcount == 0 && lane == 0) tr[51] = clk64();
+                }
             }
+            u += sg.s1 - sg.s0;
         }
     }
     else if (warp == X_PRODUCER_WARP) {
         // ============================================================== activation TMA producer
-        if (lane == 0) {
-            pdl_wait_prior_grids();  // x may be produced by the previous kernel in the stream
-            int xcount = 0;
-            for (int u = u0; u < u1;) {
-                const int tile   = u / p.spt;
-                const int s0     = u - tile * p.spt;
-                const int s1     = min(p.spt, s0 + (u1 - u));
-                const int t_tile = tile / p.n_tiles;
-                for (int st = s0; st < s1; ++st) {
+        pdl_wait_prior_grids();  // x may be produced by the previous kernel in the stream
+        int xcount = 0;
+        for (int u = u0; u < u1;) {
+            const Segment sg = segment_at(p, u, u1);
+            for (int st = sg.s0; st < sg.s1; ++st) {
 #pragma unroll 1
-                    for (int xi = 0; xi < XSTEPS; ++xi, ++xcount) {
-                        const int xs       = xcount % XS;
-                        const uint32_t xph = (xcount / XS) & 1;
-                        mbar_wait(xempty_bar + 8 * xs, xph ^ 1);
+                for (int xi = 0; xi < XSTEPS; ++xi, ++xcount) {
+                    const int xs       = xcount % XS;
+                    const uint32_t xph = (xcount / XS) & 1;
+                    mbar_wait(xempty_bar + 8 * xs, xph ^ 1);
+                    if (elect_one_sync()) {
                         mbar_arrive_expect_tx(xfull_bar + 8 * xs, X_STAGE);
 #pragma unroll
                         for (int j = 0; j < XSUB; ++j)
                             tma_load_2d(x_base + xs * X_STAGE + j * X_BOX, &map_x, xfull_bar + 8 * xs,
-                                        st * STAGE_K + (xi * XSUB + j) * SUB_K, t_tile * BT);
+                                        st * STAGE_K + (xi * XSUB + j) * SUB_K, sg.t_tile * BT);
                     }
+                    __syncwarp();
                 }
-                u += s1 - s0;
             }
+            u += sg.s1 - sg.s0;
         }
     }
     else if (warp == MMA_WARP) {
-        // ============================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            int acount = 0, xcount = 0, seg = 0;
-            for (int u = u0; u < u1; ++seg) {
-                const int tile = u / p.spt;
-                const int s0   = u - tile * p.spt;
-                const int s1   = min(p.spt, s0 + (u1 - u));
-                const int d    = seg % ND;
-                mbar_wait(tempty_bar + 8 * d, ((seg / ND) & 1) ^ 1);  // the epilogue has drained this accumulator
+        // ============================================================== MMA issuer (whole warp loops, one lane issues)
+        int acount = 0, xcount = 0, seg = 0;
+        for (int u = u0; u < u1; ++seg) {
+            const Segment sg = segment_at(p, u, u1);
+            const int d      = seg % ND;
+            mbar_wait(tempty_bar + 8 * d, ((seg / ND) & 1) ^ 1);  // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + uint32_t(d * BT);
+            for (int st = sg.s0; st < sg.s1; ++st, ++acount) {
+                const int a        = acount % A_STAGES;
+                const uint32_t aph = (acount / A_STAGES) & 1;
+                mbar_wait(afull_bar + 8 * a, aph);  // 256 k of dequantised weights sit in TMEM
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + uint32_t(d * BT);
-                for (int st = s0; st < s1; ++st, ++acount) {
-                    const int a        = acount % A_STAGES;
-                    const uint32_t aph = (acount / A_STAGES) & 1;
-                    mbar_wait(afull_bar + 8 * a, aph);  // 256 k of dequantised weights sit in TMEM
-                    tc_fence_after();
-                    const uint32_t a_addr = tmem_base + uint32_t(A_COL0 + a * A_STAGE_COLS);
+                const uint32_t a_addr = tmem_base + uint32_t(A_COL0 + a * A_STAGE_COLS);
 #pragma unroll 1
-                    for (int xi = 0; xi < XSTEPS; ++xi, ++xcount) {
-                        const int xs       = xcount % XS;
-                        const uint32_t xph = (xcount / XS) & 1;
-                        mbar_wait(xfull_bar + 8 * xs, xph);  // activation boxes landed
-                        tc_fence_after();
+                for (int xi = 0; xi < XSTEPS; ++xi, ++xcount) {
+                    const int xs       = xcount % XS;
+                    const uint32_t xph = (xcount / XS) & 1;
+                    mbar_wait(xfull_bar + 8 * xs, xph);  // activation boxes landed
+                    tc_fence_after();
+                    if (elect_one_sync()) {
 #pragma unroll
                         for (int j = 0; j < XSUB; ++j) {
                             const int sub         = xi * XSUB + j;
@@ -461,192 +608,157 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
                             for (int k = 0; k < SUB_K / UMMA_K; ++k) {
                                 // A: 16 k = 8 TMEM columns per UMMA; B: +32 bytes inside the swizzle atom = +2 in the (>>4) field
                                 umma_f16_ts(d_addr, a_addr + uint32_t(sub * (SUB_K / 2) + k * (UMMA_K / 2)), b_desc + uint64_t(2 * k), IDESC,
-                                            (st > s0 || sub > 0 || k > 0) ? 1u : 0u);
+                                            (st > sg.s0 || sub > 0 || k > 0) ? 1u : 0u);
                             }
                         }
                         umma_commit(xempty_bar + 8 * xs);  // frees the activation stage once these MMAs have read it
+                        if (xi == XSTEPS - 1) {
+                            umma_commit(aempty_bar + 8 * a);  // frees the A stage
+                            if (st == sg.s1 - 1)
+                                umma_commit(tfull_bar + 8 * d);  // accumulator of this segment complete
+                        }
                     }
-                    umma_commit(aempty_bar + 8 * a);      // frees the A stage
-                    if constexpr (TRACE) {
-                        if (acount < 12) tr[16 + acount] = clk64();
-                    }
+                    __syncwarp();
                 }
-                umma_commit(tfull_bar + 8 * d);  // accumulator of this segment complete
-                u += s1 - s0;
-            }
-            if constexpr (TRACE) tr[30] = clk64();
-        }
-    }
-    else if (warp >= EPI_WARPS) {
-        // ============================================================== dequantisers: smem int8 -> registers -> TMEM
-        const int dw   = warp - EPI_WARPS;   // 0 .. DQW-1
-        const int quad = dw & 3;             // == warp % 4: the TMEM lane quadrant this warp may touch
-        const int part = dw >> 2;            // which 1/NP of the stage's k range
-        const int row  = quad * 32 + lane;   // feature row inside the tile
-        constexpr int CHUNK0 = 0;            // silence unused warnings in some instantiations
-        (void)CHUNK0;
-        const int c_first = part * CH;                    // first 16-byte chunk (of 16 per 256-k row)
-        const int box     = c_first >> 3;                 // which 128-byte-wide box
-        const int cb      = c_first & 7;                  // first chunk inside the box
-        const uint32_t row_off = uint32_t(box * W_BOX_BYTES + row * 128);
-        const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-        int wcount = 0, acount = 0;
-        for (int u = u0; u < u1;) {
-            const int tile   = u / p.spt;
-            const int s0     = u - tile * p.spt;
-            const int s1     = min(p.spt, s0 + (u1 - u));
-            const int n_tile = tile % p.n_tiles;
-            uint32_t scale2  = 0;
-            if constexpr (SCALE_IN_A) {
-                const int n      = n_tile * BLOCK_N + row;
-                const __half sv  = (n < p.N) ? static_cast<const __half*>(p.scales)[n] : __ushort_as_half(0);
-                const __half2 s2 = __half2half2(sv);
-                scale2           = *reinterpret_cast<const uint32_t*>(&s2);
-            }
-            for (int st = s0; st < s1; ++st, ++wcount, ++acount) {
-                const int ws       = wcount % WS;
-                const uint32_t wph = (wcount / WS) & 1;
-                const int a        = acount % A_STAGES;
-                const uint32_t aph = (acount / A_STAGES) & 1;
-                mbar_wait(wfull_bar + 8 * ws, wph);  // int8 stage landed
-                const uint8_t* rp = smem_gen + (w8_base - smem_base) + ws * W_STAGE + row_off;
-                uint4 in[CH];
-#pragma unroll
-                for (int j = 0; j < CH; ++j)
-                    in[j] = *reinterpret_cast<const uint4*>(rp + ((((cb + j) ^ (row & 7))) << 4));  // 128B swizzle: chunk ^ (row & 7)
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(wempty_bar + 8 * ws);  // bytes are in registers: hand the stage back to the TMA producer
-                mbar_wait(aempty_bar + 8 * a, aph ^ 1);  // the MMAs that read this A stage have completed
-                tc_fence_after();
-                const uint32_t a_col = uint32_t(A_COL0 + a * A_STAGE_COLS + c_first * 8);
-#pragma unroll
-                for (int h = 0; h < CH / 4; ++h) {
-                    uint32_t o[32];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dequant16<T>(in[h * 4 + j], scale2, &o[8 * j]);
-                    tmem_st_x32(tmem_base + lane_addr + a_col + uint32_t(h * 32), o);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(afull_bar + 8 * a);
                 if constexpr (TRACE) {
-                    if (dw == 0 && lane == 0 && acount < 12) tr[acount] = clk64();
+                    if (acount < 12 && lane == 0) tr[16 + acount] = clk64();
                 }
             }
-            u += s1 - s0;
+            u += sg.s1 - sg.s0;
+        }
+        if constexpr (TRACE) {
+            if (lane == 0) tr[30] = clk64();
         }
     }
     else {
-        // ============================================================== epilogue warps 0..3 (TMEM lane quadrant = warp)
-        const int quad = warp;
-        const int row  = quad * 32 + lane;
-        const int et   = threadIdx.x;  // 0..127
-        pdl_wait_prior_grids();        // y / workspace may still be in use by the previous kernel in the stream
-        T* y = static_cast<T*>(p.y);
-        int seg = 0;
-        for (int u = u0; u < u1; ++seg) {
-            const int tile   = u / p.spt;
-            const int s0     = u - tile * p.spt;
-            const int s1     = min(p.spt, s0 + (u1 - u));
-            const int n_tile = tile % p.n_tiles;
-            const int t_tile = tile / p.n_tiles;
-            const int d      = seg % ND;
-            const int n      = n_tile * BLOCK_N + row;
-            const bool n_ok  = n < p.N;
-            const bool contributor = s0 > 0;                 // somebody else owns this tile: dump the partial
-            const bool owner_fixup = (s0 == 0) && (s1 < p.spt);  // we own it but others hold the rest of its k range
-            float scale_f = 1.f, bias_f = 0.f;
-            if (!contributor && n_ok) {
-                if constexpr (!SCALE_IN_A)
-                    scale_f = to_float(static_cast<const T*>(p.scales)[n]);
-                if (p.bias != nullptr)
-                    bias_f = to_float(static_cast<const T*>(p.bias)[n]);
-            }
-            // contributors of an owned tile: the CTAs g+1 .. g_last whose ranges start inside this tile
-            int g_last = g;
-            if (owner_fixup) {
-                const int tile_end = (tile + 1) * p.spt;
-                while (g_last + 1 < G && unit_begin(p, g_last + 1, G) < tile_end)
-                    ++g_last;
-            }
-            mbar_wait(tfull_bar + 8 * d, (seg / ND) & 1);
-            tc_fence_after();
-            if constexpr (TRACE) {
-                if (et == 0 && seg < 4) tr[32 + 2 * seg] = clk64();
-            }
-            if (owner_fixup) {
-                // wait (normally not at all: the contributors met this tile first) until every contributor has published
-                if (et > 0 && et <= g_last - g) {
-                    while (ld_acquire_gpu(p.flags + g + et) == 0) {
-                    }
+        const bool is_epi = warp < EPI_WARPS;
+        if (!is_epi) {
+            // ========================================================== dequantisers: smem int8 -> registers -> TMEM
+            const int dw   = warp - EPI_WARPS;   // 0 .. DQW-1
+            const int quad = dw & 3;             // == warp % 4: the TMEM lane quadrant this warp may touch
+            const int part = dw >> 2;            // which 1/NP of the stage's k range
+            const int row  = quad * 32 + lane;   // feature row inside the tile
+            const int c_first = part * CH;       // first 16-byte chunk (of 16 per 256-k row)
+            const int box     = c_first >> 3;    // which 128-byte-wide box
+            const int cb      = c_first & 7;     // first chunk inside the box
+            const uint32_t row_off   = uint32_t(box * W_BOX_BYTES + row * 128);
+            const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+            int wcount = 0, acount = 0;
+            for (int u = u0; u < u1;) {
+                const Segment sg = segment_at(p, u, u1);
+                uint32_t scale2  = 0;
+                if constexpr (SCALE_IN_A) {
+                    const int n      = sg.n_tile * BLOCK_N + row;
+                    const __half sv  = (n < p.N) ? static_cast<const __half*>(p.scales)[n] : __ushort_as_half(0);
+                    const __half2 s2 = __half2half2(sv);
+                    scale2           = *reinterpret_cast<const uint32_t*>(&s2);
                 }
-                epi_bar_sync();
-            }
-            float* my_slot = p.slots + size_t(g) * (BT * BLOCK_N);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BT; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld_x16(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(d * BT + c0), r);
-                tmem_ld_wait();
-                if (c0 + 16 >= BT) {
-                    // all of this accumulator is in registers: let the MMA issuer reuse it for the next segment
+                for (int st = sg.s0; st < sg.s1; ++st, ++wcount, ++acount) {
+                    const int ws       = wcount % WS;
+                    const uint32_t wph = (wcount / WS) & 1;
+                    const int a        = acount % A_STAGES;
+                    const uint32_t aph = (acount / A_STAGES) & 1;
+                    mbar_wait(wfull_bar + 8 * ws, wph);  // int8 stage landed
+                    const uint32_t rp = w8_base + ws * W_STAGE + row_off;
+                    uint4 in[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        in[j] = lds128(rp + ((((cb + j) ^ (row & 7))) << 4));  // 128B swizzle: chunk ^ (row & 7)
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(wempty_bar + 8 * ws);
+                    mbar_wait(aempty_bar + 8 * a, aph ^ 1);  // the MMAs that read this A stage have completed
+                    tc_fence_after();
+                    const uint32_t a_col = uint32_t(A_COL0 + a * A_STAGE_COLS + c_first * 8);
+#pragma unroll
+                    for (int h = 0; h < CH / 4; ++h) {
+                        uint32_t o[32];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dequant16<T>(in[h * 4 + j], scale2, &o[8 * j]);
+                        tmem_st_x32(tmem_base + lane_addr + a_col + uint32_t(h * 32), o);
+                    }
+                    tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0)
-                        mbar_arrive(tempty_bar + 8 * d);
+                        mbar_arrive(afull_bar + 8 * a);
+                    if constexpr (TRACE) {
+                        if (dw == 0 && lane == 0 && acount < 12) tr[acount] = clk64();
+                    }
                 }
+                u += sg.s1 - sg.s0;
+            }
+        }
+        else {
+            // ========================================================== epilogue warps 0..3 (TMEM lane quadrant = warp)
+            const int et = threadIdx.x;  // 0..127
+            pdl_wait_prior_grids();      // y / workspace may still be in use by the previous kernel in the stream
+            int seg = 0;
+            for (int u = u0; u < u1; ++seg) {
+                const Segment sg = segment_at(p, u, u1);
+                u += sg.s1 - sg.s0;
+                const int d            = seg % ND;
+                const bool contributor = sg.s0 > 0;  // somebody else owns this tile: dump the partial
+                const bool fixup       = sg.s0 == 0 && sg.s1 < p.spt;
+                if (fixup)
+                    break;  // always the last segment: handled jointly below
+                mbar_wait(tfull_bar + 8 * d, (seg / ND) & 1);
+                tc_fence_after();
+                if constexpr (TRACE) {
+                    if (et == 0 && seg < 4) tr[32 + 2 * seg] = clk64();
+                }
+                epilogue_columns<T, BT, SCALE_IN_A, (DQW == 8 ? 4 : 2)>(p, sg, contributor ? 1 : 0, tmem_base + uint32_t(d * BT), warp, lane, 0, 1, g, g,
+                                                    tempty_bar + 8 * d);
                 if (contributor) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        my_slot[(c0 + j) * BLOCK_N + row] = __uint_as_float(r[j]);
-                    continue;
+                    __threadfence();
+                    epi_bar_sync();
+                    if (et == 0)
+                        st_release_gpu(p.flags + g, 1);
                 }
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    v[j] = __uint_as_float(r[j]);
-                if (owner_fixup) {
-                    for (int gg = g + 1; gg <= g_last; ++gg) {  // ascending CTA index == ascending k: deterministic sum order
-                        const float* slot = p.slots + size_t(gg) * (BT * BLOCK_N) + c0 * BLOCK_N + row;
-                        float w[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            w[j] = __ldcg(slot + j * BLOCK_N);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            v[j] += w[j];
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int t = t_tile * BT + c0 + j;
-                    if (n_ok && t < p.M) {
-                        T o = from_float<T>(v[j] * scale_f + bias_f);
-                        if (p.residual != nullptr)
-                            o = from_float<T>(to_float(o) + to_float(static_cast<const T*>(p.residual)[int64_t(t) * p.ldr + n]));
-                        y[int64_t(t) * p.ldy + n] = o;
-                    }
+                if constexpr (TRACE) {
+                    if (et == 0 && seg < 4) tr[33 + 2 * seg] = clk64();
                 }
             }
-            if (contributor) {
-                __threadfence();
-                epi_bar_sync();
-                if (et == 0)
-                    st_release_gpu(p.flags + g, 1);
+        }
+        // ============================================================== joint finish of an owned, shared tile
+        if (last_is_fixup) {
+            if (!is_epi)
+                pdl_wait_prior_grids();
+            // the last segment and its position in the accumulator ring
+            int u = u0, seg = -1;
+            Segment sg{};
+            while (u < u1) {
+                sg = segment_at(p, u, u1);
+                u += sg.s1 - sg.s0;
+                ++seg;
             }
-            else if (owner_fixup) {
-                epi_bar_sync();  // every epilogue thread has finished reading the slots
-                if (et > 0 && et <= g_last - g)
-                    p.flags[g + et] = 0;  // leave the workspace clean for the next call
+            const int d = seg % ND;
+            // contributors: the CTAs g+1 .. g_last whose ranges start inside this tile
+            int g_last         = g;
+            const int tile_end = (sg.tile + 1) * p.spt;
+            while (g_last + 1 < G && unit_begin(p, g_last + 1) < tile_end)
+                ++g_last;
+            const int jt = threadIdx.x;  // 0 .. JOINT_THREADS-1 (warps 0 .. 4+DQW-1)
+            // wait (normally not at all: the contributors met this tile FIRST) until every contributor has published
+            if (jt >= 1 && jt <= g_last - g) {
+                while (ld_acquire_gpu(p.flags + g + jt) == 0) {
+                }
             }
+            mbar_wait(tfull_bar + 8 * d, (seg / ND) & 1);
+            tc_fence_after();
+            joint_bar_sync<JOINT_THREADS>();
             if constexpr (TRACE) {
-                if (et == 0 && seg < 4) tr[33 + 2 * seg] = clk64();
+                if (jt == 0) tr[40] = clk64();
             }
-            u += s1 - s0;
+            epilogue_columns<T, BT, SCALE_IN_A, (DQW == 8 ? 4 : 2)>(p, sg, 2, tmem_base + uint32_t(d * BT), warp & 3, lane, warp >> 2, (EPI_WARPS + DQW) / 4, g,
+                                                g_last, 0u);
+            joint_bar_sync<JOINT_THREADS>();  // every thread has finished reading the slots
+            if (jt >= 1 && jt <= g_last - g)
+                p.flags[g + jt] = 0;  // leave the workspace clean for the next call
+            if constexpr (TRACE) {
+                if (jt == 0) tr[41] = clk64();
+            }
         }
     }
 
@@ -862,7 +974,8 @@ int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scal
                    int64_t ldr, void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,
                    size_t workspace_bytes, bool pdl, unsigned long long* trace, cudaStream_t stream)
 {
-    const bool have_ws = workspace != nullptr && workspace_bytes >= gemm_tc_workspace_bytes(M, N, K);
+    static const int nosplit_knob = env_int("EETQ_B200_TC_NOSPLIT", 0);  // diagnostics: whole tiles per CTA
+    const bool have_ws = nosplit_knob == 0 && workspace != nullptr && workspace_bytes >= gemm_tc_workspace_bytes(M, N, K);
     // no (or too small a) workspace: every CTA takes whole tiles -- correct, just less evenly balanced
     const TcConfig cfg = choose_config(M, N, K, have_ws);
     if (cfg.grid > kFlagRegionBytes / int(sizeof(int))) {
@@ -897,7 +1010,11 @@ int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scal
     p.n_tiles      = cfg.n_tiles;
     p.t_tiles      = cfg.t_tiles;
     p.spt          = cfg.spt;
-    p.total_units  = cfg.n_tiles * cfg.t_tiles * cfg.spt;
+    {
+        const int total = cfg.split ? cfg.n_tiles * cfg.t_tiles * cfg.spt : cfg.n_tiles * cfg.t_tiles;
+        p.units_q       = total / cfg.grid;
+        p.units_r       = total % cfg.grid;
+    }
     p.tile_aligned = cfg.split ? 0 : 1;
     p.trace        = trace;
     if (cfg.split) {

@@ -53,6 +53,7 @@ def run(M, K, N, reps=3):
         "mma_stage_issued": [med(rel(16 + i)) for i in range(12)],
         "mma_done": med(rel(30)),
         "epi_seg": [[med(rel(32 + 2 * i)), med(rel(33 + 2 * i))] for i in range(4)],
+        "joint_fixup": [med(rel(40)), med(rel(41))],
         "cta_end": med(rel(52)), "cta_end_max": max(rel(52)),
     }
     print(json.dumps(res), flush=True)
