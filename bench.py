@@ -5,7 +5,7 @@ Metric (BASELINE.json): "decode tokens/sec Llama-2-7B w8a16 @1/2/4/8 B200; GEMV 
 Workload (config.workload): random-init Llama-2-7B (hidden 4096, inter 11008, 32 layers, 32 heads, vocab 32000), every
 nn.Linear except lm_head quantised by eet_quantize, batch 1, a 1024-token synthetic prompt prefetched into the KV
 cache by a real prefill, then greedy decode.  One "step" = one decoded token (224 quantised linears as 128 fused
-streaming GEMVs + attention + fp16 lm_head).  Each step streams ~6.5 GB of int8 weights, far more than the 126 MB L2,
+streaming GEMVs + 32 attention launches + one final-norm/lm_head/arg-max launch).  Each step streams ~6.5 GB of int8 weights, far more than the 126 MB L2,
 so no explicit L2 flush is needed between steps (config.l2 says so).
 
   value      device-resident decode: K CUDA-graph replays back to back, token fed back on the device
@@ -14,7 +14,8 @@ so no explicit L2 flush is needed between steps (config.l2 says so).
   roofline   the streaming GEMV (w8a16_gemv_kernel), timed live with CUDA events over all 128 GEMV launches of one token
   cpu_baseline  EETQ-style dequantise -> torch.matmul on the host cores (oracle.cpu_dequant_matmul), bounded sample
 
-N > 1 (torchrun): every linear column-sharded over the ranks, activations all-gathered after each linear (strong scaling).
+N > 1 (torchrun): every linear column-sharded over the ranks, attention sharded by head, lm_head by vocabulary; the activation
+vectors are exchanged by the producing kernels' epilogues over NVLink (LL words, see eetq_b200/decode.py) -- strong scaling.
 --impl reference: the reference's CPU dequant->matmul path on the host cores (rank 0 only).
 """
 from __future__ import annotations
@@ -152,10 +153,32 @@ def best_cpu_threads(s):
     return best
 
 
-def cpu_tokens_per_s(s, t_layer):
-    # lm_head (fp16, not quantised) is a plain matmul on pre-existing fp16 weights; its cost is small next to 32 layers of
-    # dequantisation and is left out of the CPU figure (stated in `sample`)
-    return 1.0 / (s.layers * t_layer)
+def cpu_lm_head_time(s, threads: int):
+    """Seconds for the fp16 lm_head matmul (weights pre-existing fp16, computed in fp32 like the rest of the CPU arm)."""
+    torch.set_num_threads(threads)
+    w = torch.randn(s.vocab, s.hidden)
+    x = torch.randn(1, s.hidden)
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        torch.matmul(x, w.t())
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_tokens_per_s(s, t_layer, t_lm_head):
+    return 1.0 / (s.layers * t_layer + t_lm_head)
+
+
+def bench_config(args, s, world, exchange):
+    """`config` of the JSON line -- identical for our arm and the reference arm (same metric, same workload)."""
+    par = "single-gpu" if world == 1 else (f"column-sharded linears + head-sharded attention + vocab-sharded lm_head x{world}; activations exchanged "
+                                           + ("by LL words pushed over NVLink from the producing kernels' epilogues (fused all-gather)"
+                                              if exchange == "ll" else "by ncclAllGather"))
+    return {"workload": f"{s.name} eet_quantize w8a16, batch 1, prompt {args.prompt} (real prefill), greedy decode",
+            "model": s.name, "global_batch": 1, "seq_len": args.prompt, "ctx_at_end": args.prompt + args.warmup + args.steps,
+            "parallelism": par, "pdl": not args.no_pdl, "cuda_graph": True,
+            "l2": "each step streams the rank's int8 weights (>= 0.8 GB per GPU, >> 126 MB L2): inputs larger than L2, no flush"}
 
 
 def run_reference(args):
@@ -163,23 +186,29 @@ def run_reference(args):
     if rank != 0:
         return 0
     s = shape_of(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = best_cpu_threads(s)
-    # one step = the 7 linears of one decoder layer (1/layers of a token): a bounded sample, so that K steps + W warm-up
-    # steps end within minutes on the host cores
+    # one step = a bounded sample of one token: the 7 quantised linears of ONE decoder layer (1/layers of a token), so
+    # that K steps + W warm-up steps end within minutes on the host cores; ms_per_step is the REAL time of that step
     steps, warm = args.steps, args.warmup
     if warm:
         cpu_layer_time(s, warm, threads)
+    t0 = time.perf_counter()
     t_layer = cpu_layer_time(s, steps, threads)
-    tps = cpu_tokens_per_s(s, t_layer)
+    wall = time.perf_counter() - t0
+    t_lm = cpu_lm_head_time(s, threads)
+    tps = cpu_tokens_per_s(s, t_layer, t_lm)
+    exchange = os.environ.get("EETQ_B200_EXCHANGE", "ll") if world > 1 else "none"
+    sample = (f"each step = the 7 quantised linears of 1 of {s.layers} decoder layers (EETQ-style dequant q.half()*s then torch.matmul, every "
+              f"call; thread pool = fastest of 8/16/32/64/all); median step {t_layer * 1e3:.1f} ms; tokens/s = 1 / ({s.layers} x step + "
+              f"lm_head {t_lm * 1e3:.1f} ms); attention excluded (negligible on the CPU next to the dequantisation)")
     line = {
         "impl": "reference", "metric": "decode_tokens_per_sec", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1e3 / tps, "higher_is_better": True, "scaling": "strong",
+        "steps": steps, "warmup": warm, "ms_per_step": wall * 1e3 / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"{s.name} w8a16 decode, batch 1, M=1 linears", "model": s.name, "parallelism": "cpu"},
-        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                         "sample": f"(thread pool size picked as the fastest of 8/16/32/64/all) 7 quantised linears of 1 of {s.layers} decoder layers per step (dequant q.half()*s then "
-                                   f"torch.matmul, every call), median of {steps}; tokens/s = 1/({s.layers} x layer time); "
-                                   "fp16 lm_head and attention excluded"},
+        "config": bench_config(args, s, world, exchange),
+        "step_is": f"1/{s.layers} of a token (one decoder layer's linears); value is scaled to whole tokens",
+        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference has no CPU forward and its GPU kernels refuse sm>=90; this is the north-star CPU path "
                 "(EETQ-style dequantise -> torch.matmul, examples/layers/test_w8a16_gemm.py:44-47) via oracle/w8a16_oracle.py",
@@ -217,24 +246,53 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_quant = time.perf_counter() - t0
     dec = W8A16LlamaDecoder.from_model(model, max_ctx=ctx_max, pdl=not args.no_pdl, rank=rank, world_size=world)
-    del model
-    torch.cuda.empty_cache()
 
-    # synthetic prompt, real prefill through the batched tcgen05 kernels
+    # synthetic prompt, real prefill through the batched tcgen05 kernels (cold = first call: lazy module loads, tensor-map
+    # encodes, workspace allocation; warm = the same prompt again)
     g = torch.Generator(device=dev).manual_seed(11)
     prompt = torch.randint(0, s.vocab, (args.prompt,), generator=g, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    dec.prefill(prompt)
-    e1.record()
-    torch.cuda.synchronize()
-    prefill_ms = e0.elapsed_time(e1)
-    dec.capture()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    barrier()
+    e0.record()
+    dec.prefill(prompt)
+    e1.record()
+    torch.cuda.synchronize()
+    prefill_cold_ms = e0.elapsed_time(e1)
+    barrier()
+    e0.record()
+    first_token = dec.prefill(prompt)
+    e1.record()
+    torch.cuda.synchronize()
+    prefill_ms = e0.elapsed_time(e1)
+
+    # N > 1: the sharded decoder must generate exactly the single-GPU tokens (rank 0 also runs an unsharded decoder)
+    tokens_match = None
+    n_check = min(16, args.steps)
+    if world > 1:
+        ref_tokens = None
+        if rank == 0:
+            single = W8A16LlamaDecoder.from_model(model, max_ctx=ctx_max, pdl=not args.no_pdl, rank=0, world_size=1)
+            ref_tokens = single.generate(prompt, n_check + 1)
+            del single
+        got = [int(first_token.item())]
+        dec.capture()
+        for _ in range(n_check):
+            dec.step()
+            got.append(int(dec.token.item()))
+        if rank == 0:
+            tokens_match = bool(got == ref_tokens)
+        barrier()
+        dec.prefill(prompt)   # rewind to the end of the prompt
+    del model
+    torch.cuda.empty_cache()
+    if dec.graph is None:
+        dec.capture()
 
     # ------------------------------------------------------------------ value: device-resident decode
     for _ in range(args.warmup):
@@ -283,67 +341,81 @@ def run_ours(args):
     e2e_tps = args.steps / e2e_s
 
     # ------------------------------------------------------------------ roofline of the dominant kernel (streaming GEMV)
-    # all GEMV launches of one token (4 fused GEMVs x layers, each on its own weights => working set >> L2), own graph
-    def gemv_only():
-        H, I = s.hidden, s.inter
-        for w in dec.layers:
-            dec._gemv(dec.x, H, w["qkv"], dec.qkv, norm_w=w["ln1"], xmode=1)
-            dec._gemv(dec.attn, H, w["o"], dec.x2, residual_full=dec.x)
-            dec._gemv(dec.x2, H, w["gu"], dec.gu, norm_w=w["ln2"], xmode=1)
-            dec._gemv(dec.gu, 2 * I, w["down"], dec.x, xmode=2, residual_full=dec.x2)
+    # all GEMV launches of one token on THIS rank's shards (4 fused GEMVs x layers, each on its own weights => working set
+    # >> L2), captured as their own graph over plain scratch vectors (no exchange) and timed with CUDA events
+    H, I = s.hidden, s.inter
+    sx, sx2 = torch.randn(H, device=dev).half(), torch.randn(H, device=dev).half()
+    sattn, sact = torch.randn(H, device=dev).half(), torch.randn(I, device=dev).half()
+    sqkv = torch.zeros(3 * dec.Hl, dtype=torch.float16, device=dev)
+    n0, i0 = dec.plan["hidden"][0], dec.plan["inter"][0]
 
-    roof = None
-    if world == 1:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            gemv_only()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        gg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gg):
-            gemv_only()
-        for _ in range(3):
-            gg.replay()
-        torch.cuda.synchronize()
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            gg.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        n_launch = 4 * s.layers
-        us_per_launch = e0.elapsed_time(e1) * 1e3 / (reps * n_launch)
-        H, I = s.hidden, s.inter
-        per_layer = [(H, 3 * H), (H, H), (H, 2 * I), (I, H)]  # (K, N) of the 4 fused GEMVs
-        bytes_per_launch = sum(K * N + 2 * N + 2 * K + 2 * N for K, N in per_layer) / 4.0
-        achieved = bytes_per_launch / us_per_launch / 1e3  # GB/s
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        # DRAM traffic per launch from the committed `ncu --set full` capture of the four decode GEMV shapes
-        # (profiles/r01_ncu_full_summary.md: dram__bytes_read.sum + dram__bytes_write.sum = 16.83 / 50.41 / 94.16 / 45.17 MB for
-        # o / q|k|v-sized / gate|up / down), averaged per launch like `achieved`; null for other models
-        traffic = (16.834e6 + 50.415e6 + 94.158e6 + 45.173e6) / 4.0 if (s.hidden, s.inter) == (4096, 11008) else None
-        roof = {"bound": "hbm", "kernel": "w8a16_gemv_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_ncu_full_summary.md (ncu --set full)",
-                "us_per_launch": us_per_launch, "bytes_per_launch": bytes_per_launch,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "how": f"CUDA events around {reps} replays of a graph holding the {n_launch} GEMV launches of one token "
-                       "(each on its own layer's weights, 6.5 GB working set)"}
+    def gemv_only():
+        for w in dec.layers:
+            sl = slice(n0, n0 + w["o"].N)
+            dec._gemv(sx, H, w["qkv"], sqkv, norm_w=w["ln1"], xmode=1)
+            dec._gemv(sattn, H, w["o"], sx2[sl], residual=sx[sl])
+            dec._gemv(sx2, H, w["gu"], sact[i0:i0 + dec.Il], norm_w=w["ln2"], xmode=1, epi=1)
+            dec._gemv(sact, I, w["down"], sx[sl], residual=sx2[sl])
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        gemv_only()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gg):
+        gemv_only()
+    for _ in range(3):
+        gg.replay()
+    torch.cuda.synchronize()
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        gg.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    n_launch = 4 * s.layers
+    us_per_launch = e0.elapsed_time(e1) * 1e3 / (reps * n_launch)
+    w0_ = dec.layers[0]
+    # algorithmic bytes: K*N weights + 2N scales + 2K activations + 2 x outputs
+    per_layer = [(w0_["qkv"].K, w0_["qkv"].N, w0_["qkv"].N), (w0_["o"].K, w0_["o"].N, w0_["o"].N), (w0_["gu"].K, w0_["gu"].N, w0_["gu"].N // 2),
+                 (w0_["down"].K, w0_["down"].N, w0_["down"].N)]
+    bytes_per_launch = sum(K * N + 2 * N + 2 * K + 2 * outs for K, N, outs in per_layer) / 4.0
+    achieved = bytes_per_launch / us_per_launch / 1e3  # GB/s
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM traffic per launch of this kernel from the committed `ncu --set full` capture (profiles/gemv_traffic.json, written by
+    # tools/gemv_traffic.py: dram__bytes_read.sum + dram__bytes_write.sum averaged over the four decode GEMV shapes), or null
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "gemv_traffic.json")))
+        ent = tj.get(f"{s.name}/world{world}")
+        if ent:
+            traffic, traffic_src = float(ent["bytes_per_launch"]), f"profiles/gemv_traffic.json ({ent.get('source', 'ncu --set full')}, commit {ent.get('commit', '?')})"
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "w8a16_gemv_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "us_per_launch": us_per_launch, "bytes_per_launch": bytes_per_launch, "rank": rank,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "how": f"CUDA events around {reps} replays of a graph holding the {n_launch} GEMV launches of one token on this rank's shards "
+                   f"(each on its own layer's weights, {dec.weight_bytes_per_token() / 1e9:.2f} GB working set)"}
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1, bounded sample)
     cpu = None
     if world == 1 and not args.skip_cpu_baseline:
         threads = best_cpu_threads(s)
         t_layer = cpu_layer_time(s, 5, threads)
-        cpu = {"value": cpu_tokens_per_s(s, t_layer), "unit": "tokens/s", "cores": threads, "kind": "port",
+        t_lm = cpu_lm_head_time(s, threads)
+        cpu = {"value": cpu_tokens_per_s(s, t_layer, t_lm), "unit": "tokens/s", "cores": threads, "kind": "port",
                "sample": f"7 quantised linears of 1 of {s.layers} decoder layers (EETQ-style dequant q.half()*s -> torch.matmul "
-                         f"per call, oracle.cpu_dequant_matmul), median of 5; tokens/s = 1/({s.layers} x {t_layer * 1e3:.0f} ms); "
-                         "fp16 lm_head and attention excluded"}
+                         f"per call, oracle.cpu_dequant_matmul), median of 5; tokens/s = 1/({s.layers} x {t_layer * 1e3:.0f} ms + lm_head "
+                         f"{t_lm * 1e3:.1f} ms); attention excluded"}
 
     if rank == 0:
         wbytes = dec.weight_bytes_per_token()
@@ -351,12 +423,7 @@ def run_ours(args):
             "metric": "decode_tokens_per_sec", "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": f"{s.name} eet_quantize w8a16, batch 1, prompt {args.prompt} (real prefill), greedy decode",
-                       "model": s.name, "global_batch": 1, "seq_len": args.prompt, "ctx_at_end": args.prompt + args.warmup + args.steps,
-                       "parallelism": "single-gpu" if world == 1 else f"column-sharded linears x{world} + all-gather of activations "
-                                      + ("fused into the GEMV epilogue over NVLink peer stores" if dec.allgather == "p2p" else "by ncclAllGather"),
-                       "l2": "each step streams %.2f GB of int8 weights per GPU (>> 126 MB L2): inputs larger than L2, no flush" % (wbytes / 1e9),
-                       "pdl": not args.no_pdl, "cuda_graph": True},
+            "config": bench_config(args, s, world, dec.exchange),
             "clocks": clocks,
             "e2e": {"value": e2e_tps, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
                     "api": "W8A16LlamaDecoder.step_host(pinned token) -> pinned next token, synchronised every step"},
@@ -364,8 +431,10 @@ def run_ours(args):
             "launches_per_step": int(dec.launches_per_step),
             "roofline": roof,
             "cpu_baseline": cpu,
-            "weights_only_roofline_tokens_per_s": (float(roof["peak"]) * 1e9 / wbytes) if roof else None,
-            "prefill_ms": prefill_ms, "build_s": t_build, "quantize_s": t_quant,
+            "weights_only_roofline_tokens_per_s": float(roof["peak"]) * 1e9 / wbytes,
+            "weight_bytes_per_token_per_gpu": wbytes,
+            "tokens_match_single_gpu": tokens_match,
+            "prefill_ms": prefill_ms, "prefill_cold_ms": prefill_cold_ms, "build_s": t_build, "quantize_s": t_quant,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -20,11 +20,23 @@ GEMV_MAX_M = 8
 _lib: Optional[ctypes.CDLL] = None
 
 
-class GemvPhase(ctypes.Structure):
-    """eetq_b200_gemv_phase (include/eetq_b200.h)"""
-    _fields_ = [("x", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("w", ctypes.c_void_p), ("scales", ctypes.c_void_p),
-                ("y", ctypes.c_void_p), ("N", ctypes.c_int64), ("K", ctypes.c_int64), ("norm_weight", ctypes.c_void_p),
-                ("residual", ctypes.c_void_p), ("eps", ctypes.c_float), ("xmode", ctypes.c_int)]
+class LL(ctypes.Structure):
+    """eetq_b200_ll (include/eetq_b200.h): which exchange an LL buffer currently carries"""
+    _fields_ = [("step", ctypes.c_void_p), ("per_step", ctypes.c_int), ("index", ctypes.c_int)]
+
+
+class LLPush(ctypes.Structure):
+    """eetq_b200_ll_push"""
+    _fields_ = [("world", ctypes.c_int), ("peers", ctypes.POINTER(ctypes.c_uint64)), ("local", ctypes.c_void_p),
+                ("elem_off", ctypes.c_int64), ("step", ctypes.c_void_p), ("per_step", ctypes.c_int), ("index", ctypes.c_int)]
+
+
+class GemvOpts(ctypes.Structure):
+    """eetq_b200_gemv_opts"""
+    _fields_ = [("norm_weight", ctypes.c_void_p), ("eps", ctypes.c_float), ("xmode", ctypes.c_int), ("epi", ctypes.c_int),
+                ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int64), ("x_ll", ctypes.POINTER(LL)), ("residual_ll", ctypes.POINTER(LL)),
+                ("residual_off", ctypes.c_int64), ("push", ctypes.POINTER(LLPush))]
+
 
 _c_i64 = ctypes.c_int64
 _c_vp = ctypes.c_void_p
@@ -52,21 +64,19 @@ SIGNATURES = {
     "eetq_b200_w8a16_gemm_trace_info": (_c_int, [_c_i64, _c_i64, _c_i64, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)]),
     "eetq_b200_w8a16_gemm_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int,
                                            _c_vp, _c_sz, _c_vp]),
-    "eetq_b200_w8a16_gemv_fused": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp, _c_i64, _c_vp,
-                                            _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
-    "eetq_b200_w8a16_gemv_fused_p2p": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp, _c_i64, _c_i64, _c_i64,
-                                                _c_i64, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
-    "eetq_b200_decode_rmsnorm_p2p": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
-    "eetq_b200_decode_attention_p2p": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
-                                                _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
-    "eetq_b200_w8a16_gemv_fused_kvprefetch": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp, _c_i64, _c_vp, _c_i64,
-                                                       _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
-    "eetq_b200_w8a16_gemv_chain": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_int, _c_vp]),
-    "eetq_b200_decode_embed": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
-    "eetq_b200_decode_rmsnorm": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_int, _c_vp]),
-    "eetq_b200_decode_attention_splits": (_c_i64, [_c_i64]),
-    "eetq_b200_decode_attention": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
+    "eetq_b200_w8a16_gemv_fused": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int,
+                                            ctypes.POINTER(GemvOpts), _c_int, _c_vp]),
+    "eetq_b200_decode_embed": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, ctypes.POINTER(LL), _c_int, _c_vp]),
+    "eetq_b200_rmsnorm": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, ctypes.c_float, _c_int, _c_vp]),
+    "eetq_b200_layernorm_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_vp]),
+    "eetq_b200_rotary_embedding_neox": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp]),
+    "eetq_b200_prefill_rope_kv": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp]),
+    "eetq_b200_silu_mul": (_c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp]),
+    "eetq_b200_decode_attention": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, ctypes.POINTER(LLPush),
                                             _c_int, _c_vp]),
+    "eetq_b200_lm_head_scratch_bytes": (_c_sz, []),
+    "eetq_b200_lm_head_argmax": (_c_int, [_c_vp, ctypes.POINTER(LL), _c_vp, ctypes.c_float, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp,
+                                          _c_vp, _c_vp, ctypes.POINTER(LLPush), _c_int, _c_int, _c_vp]),
 }
 
 

@@ -50,8 +50,6 @@ const DeviceInfo& device_info()
     return infos[dev];
 }
 
-namespace {
-
 int check_arch()
 {
     const DeviceInfo& di = device_info();
@@ -81,7 +79,21 @@ int check_kn(const char* who, int64_t K, int64_t N)
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-}  // namespace
+// shared argument validation of every w8a16 forward entry point
+int check_forward_args(const char* who, const void* x, int64_t ldx, const void* w, const void* scales, const void* y, int64_t ldy,
+                       int64_t M, int64_t N, int64_t K, int dtype)
+{
+    EB_CHECK_ARG(x && w && scales && y, "%s: null pointer argument", who);
+    EB_CHECK_ARG(dtype == EETQ_B200_F16 || dtype == EETQ_B200_BF16, "%s: dtype must be F16 or BF16 (got %d)", who, dtype);
+    EB_CHECK_ARG(M >= 0 && M <= (int64_t(1) << 24), "%s: bad M=%lld", who, (long long)M);
+    if (int rc = check_kn(who, K, N))
+        return rc;
+    EB_CHECK_ARG(ldx >= K && ldy >= N, "%s: ldx (%lld) < K or ldy (%lld) < N", who, (long long)ldx, (long long)ldy);
+    EB_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0, "%s: ldx and ldy must be multiples of 8 elements", who);
+    EB_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y), "%s: x, w and y must be 16-byte aligned", who);
+    return EETQ_B200_OK;
+}
+
 }  // namespace eetq_b200
 
 using namespace eetq_b200;
@@ -162,21 +174,6 @@ size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K)
 }
 
 namespace {
-// shared argument validation of every w8a16 forward entry point
-int check_forward_args(const char* who, const void* x, int64_t ldx, const void* w, const void* scales, const void* y, int64_t ldy,
-                       int64_t M, int64_t N, int64_t K, int dtype)
-{
-    EB_CHECK_ARG(x && w && scales && y, "%s: null pointer argument", who);
-    EB_CHECK_ARG(dtype == EETQ_B200_F16 || dtype == EETQ_B200_BF16, "%s: dtype must be F16 or BF16 (got %d)", who, dtype);
-    EB_CHECK_ARG(M >= 0 && M <= (int64_t(1) << 24), "%s: bad M=%lld", who, (long long)M);
-    if (int rc = check_kn(who, K, N))
-        return rc;
-    EB_CHECK_ARG(ldx >= K && ldy >= N, "%s: ldx (%lld) < K or ldy (%lld) < N", who, (long long)ldx, (long long)ldy);
-    EB_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0, "%s: ldx and ldy must be multiples of 8 elements", who);
-    EB_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y), "%s: x, w and y must be 16-byte aligned", who);
-    return EETQ_B200_OK;
-}
-
 bool use_v1()
 {
 #ifdef EETQ_B200_WITH_V1
@@ -224,7 +221,7 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
         use_gemv = false;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (use_gemv && M >= 2 && gemv_mma_on() && gemv_mma_supported(int(M), K))
+    if (use_gemv && M >= 3 && gemv_mma_on() && gemv_mma_supported(int(M), K))  // M = 2: the SIMT kernel measured faster
         return launch_gemv_mma(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, pdl, s);
     if (use_gemv) {
         GemvExtras ex;
@@ -239,6 +236,60 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
     return launch_gemm_tc(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, M, N, K, dtype, workspace, workspace_bytes, pdl, trace, s);
 }
 }  // namespace
+
+// The decode GEMV (M <= 8) with its fusions exposed; see eetq_b200_gemv_opts in the header.
+int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias, void* y,
+                               int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, const eetq_b200_gemv_opts* o, int pdl,
+                               void* stream)
+{
+    EB_CHECK_ARG(o != nullptr, "w8a16_gemv_fused: null options");
+    const bool x_ll = o->x_ll != nullptr && o->x_ll->step != nullptr;
+    const bool push = o->push != nullptr && o->push->world > 0;
+    // LL buffers are 8-byte words, not element vectors: validate what applies
+    void* y_chk     = push ? const_cast<int8_t*>(w_b200) : y;
+    const int64_t kx = (o->xmode == GEMV_X_SILU_MUL) ? 2 * K : K;
+    if (int rc = check_forward_args("w8a16_gemv_fused", x, x_ll ? K : ldx, w_b200, scales, y_chk, push ? N : ldy, M, N, K, dtype))
+        return rc;
+    EB_CHECK_ARG(M >= 1 && M <= EETQ_B200_GEMV_MAX_M, "w8a16_gemv_fused: M must be in [1, %d]", EETQ_B200_GEMV_MAX_M);
+    EB_CHECK_ARG(o->xmode >= 0 && o->xmode <= 2 && (o->xmode != GEMV_X_RMSNORM || (o->norm_weight != nullptr && aligned16(o->norm_weight))),
+                 "w8a16_gemv_fused: bad xmode / norm_weight");
+    EB_CHECK_ARG(x_ll || ldx >= kx, "w8a16_gemv_fused: ldx too small for the activation mode");
+    EB_CHECK_ARG(o->epi == GEMV_EPI_PLAIN || o->epi == GEMV_EPI_SILU_PAIRS, "w8a16_gemv_fused: bad epilogue mode");
+    EB_CHECK_ARG(!(x_ll && o->xmode == GEMV_X_SILU_MUL), "w8a16_gemv_fused: LL input cannot be combined with the SiLU-mul prologue");
+    if (int rc = check_arch())
+        return rc;
+    GemvExtras ex;
+    ex.norm_weight = o->norm_weight;
+    ex.eps         = o->eps;
+    ex.xmode       = o->xmode;
+    ex.epi         = o->epi;
+    ex.residual    = o->residual;
+    ex.ldr         = o->ldr;
+    if (x_ll) {
+        ex.x_ll.tag_base = static_cast<const int*>(o->x_ll->step);
+        ex.x_ll.per_step = o->x_ll->per_step;
+        ex.x_ll.index    = o->x_ll->index;
+    }
+    if (o->residual_ll != nullptr && o->residual_ll->step != nullptr) {
+        EB_CHECK_ARG(o->residual != nullptr, "w8a16_gemv_fused: residual_ll without a residual buffer");
+        ex.res_ll.tag_base = static_cast<const int*>(o->residual_ll->step);
+        ex.res_ll.per_step = o->residual_ll->per_step;
+        ex.res_ll.index    = o->residual_ll->index;
+        ex.res_off         = int(o->residual_off);
+    }
+    if (push) {
+        EB_CHECK_ARG(o->push->world <= 8 && o->push->peers != nullptr && o->push->step != nullptr, "w8a16_gemv_fused: bad LL push");
+        ex.push.world = o->push->world;
+        for (int r = 0; r < o->push->world; ++r)
+            ex.push.peer[r] = o->push->peers[r];
+        ex.push.local        = static_cast<unsigned long long*>(o->push->local);
+        ex.push.elem_off     = int(o->push->elem_off);
+        ex.push.tag.tag_base = static_cast<const int*>(o->push->step);
+        ex.push.tag.per_step = o->push->per_step;
+        ex.push.tag.index    = o->push->index;
+    }
+    return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl != 0, static_cast<cudaStream_t>(stream));
+}
 
 int eetq_b200_w8a16_gemm_ex(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
                             void* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace,

@@ -53,54 +53,85 @@ int launch_from_ref_layout(const uint8_t* w_ref, int64_t K, int64_t N, int8_t* q
 int launch_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t* w_ref, cudaStream_t stream);
 
 enum { GEMV_X_PLAIN = 0, GEMV_X_RMSNORM = 1, GEMV_X_SILU_MUL = 2 };
-// Fused all-gather over NVLink peer memory (column-sharded linears): instead of writing its output
-// slice locally and calling NCCL, the GEMV epilogue stores the slice into EVERY rank's activation buffer (peer-mapped
-// symmetric memory), then the last CTA publishes a per-call epoch flag on every peer and waits until all peers' flags
-// for the same call have arrived -- when the kernel completes, the full activation vector is present on this rank.
-struct GemvP2P {
-    unsigned long long peer_y[8]    = {};  // rank p's output buffer, already offset to THIS rank's first row
-    unsigned long long peer_flag[8] = {};  // address, on rank p, of flags[slot][this rank]
-    const unsigned* local_flags     = nullptr;  // this rank's flags[slot][0..world)
-    unsigned* ticket                = nullptr;  // local CTA ticket (zero between calls)
-    const int* epoch                = nullptr;  // device counter, strictly increasing per decode step
-    int world                       = 1;
-    // consumer side: flags of the call that produced THIS kernel's input (all ranks must have published `*epoch` there
-    // before the activation is read); nullptr = the input was produced locally
-    const unsigned* wait_flags      = nullptr;
+enum { GEMV_EPI_PLAIN = 0, GEMV_EPI_SILU_PAIRS = 1 };
+
+// ---- "LL" exchange of small vectors between ranks (column-sharded multi-GPU decode) -------------
+// A vector of E fp16 values travels as E/2 8-byte words {value pair, 32-bit tag}.  The producer stores each word with ONE
+// 8-byte store (single-copy atomic) straight into every rank's copy of the buffer (peer-mapped symmetric memory, NVLink);
+// the consumer polls the words it needs until their tag equals the tag of the exchange.  Data and flag arrive together, so
+// there is no fence, no separate flag and no collective on the critical path.  tag = step * per_step + index + 1: `step` is a
+// device counter that the last kernel of a decode step increments, `index` numbers the exchanges inside a step; a buffer is
+// only rewritten several exchanges later, when (by the data dependencies of the layer chain) every rank has consumed it.
+struct LLTag {
+    const int* tag_base = nullptr;  // device step counter; nullptr = not an LL buffer
+    int per_step        = 0;
+    int index           = 0;
 };
+struct LLPush {
+    unsigned long long peer[8] = {};      // base address of the LL buffer on every rank (index = rank), peer-mapped
+    unsigned long long* local  = nullptr; // this rank's own copy (for consumers inside the same kernel)
+    int elem_off               = 0;       // first element of this rank's slice inside the full vector
+    int world                  = 0;       // 0 = no push
+    LLTag tag;
+};
+__device__ __forceinline__ uint32_t ll_tag(const LLTag& t)
+{
+    return uint32_t(*t.tag_base) * uint32_t(t.per_step) + uint32_t(t.index) + 1u;
+}
+__device__ __forceinline__ unsigned long long ll_pack(uint32_t data, uint32_t tag)
+{
+    return (static_cast<unsigned long long>(tag) << 32) | data;
+}
+// word index is relative to this rank's slice (elem_off / 2 is added)
+__device__ __forceinline__ void ll_push_word(const LLPush& p, int local_word, uint32_t data)
+{
+    const unsigned long long v   = ll_pack(data, ll_tag(p.tag));
+    const unsigned long long off = (static_cast<unsigned long long>(p.elem_off >> 1) + static_cast<unsigned long long>(local_word)) * 8ull;
+#pragma unroll 1
+    for (int r = 0; r < p.world; ++r)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.peer[r] + off), "l"(v) : "memory");
+}
+// N (even) consecutive LL words -> their N data halves; spins until all tags match
+template <int N>
+__device__ __forceinline__ void ll_load_words(const unsigned long long* src, uint32_t tag, uint32_t (&out)[N])
+{
+    static_assert(N % 2 == 0, "pairs of words (16-byte loads)");
+    unsigned long long v[N];
+    bool ok;
+    do {
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(v[i]), "=l"(v[i + 1]) : "l"(src + i) : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            ok = ok && (uint32_t(v[i] >> 32) == tag);
+    } while (!ok);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        out[i] = uint32_t(v[i] & 0xffffffffull);
+}
+
 struct GemvExtras {
     const void* norm_weight = nullptr;  // [K], GEMV_X_RMSNORM
-    const void* residual    = nullptr;  // [M, N] row stride ldr
+    const void* residual    = nullptr;  // [M, N] row stride ldr, or LL words (res_ll)
     int64_t ldr             = 0;
     float eps               = 0.f;
     int xmode               = GEMV_X_PLAIN;
-    GemvP2P p2p;
-    // optional L2 prefetch issued by the GEMV CTAs once their own weight stream is fully in flight: the KV cache rows
-    // [0, *pf_pos) of every head (layout [heads][max_ctx][128] fp16) that the NEXT kernel (attention) will read
-    const void* pf_k   = nullptr;
-    const void* pf_v   = nullptr;
-    const int* pf_pos  = nullptr;
-    int pf_heads       = 0;
-    int pf_max_ctx     = 0;
+    int epi                 = GEMV_EPI_PLAIN;
+    LLTag x_ll;     // x is an LL buffer of the full K-vector
+    LLTag res_ll;   // residual is an LL buffer of the full output vector; this rank's slice starts at element res_off
+    int res_off = 0;
+    LLPush push;    // outputs go to every rank's LL buffer instead of y
 };
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
                 int M, int64_t N, int64_t K, int dtype, const GemvExtras& ex, bool pdl, cudaStream_t stream);
 
-// one phase of a chained decode GEMV launch (M = 1, fp16); mirrors eetq_b200_gemv_phase in the public header
-struct GemvChainPhase {
-    const void* x;
-    int64_t ldx;
-    const void* w;
-    const void* scales;
-    void* y;
-    int64_t N;
-    int64_t K;
-    const void* norm_weight;
-    const void* residual;
-    float eps;
-    int xmode;
-};
-int launch_gemv_chain(const GemvChainPhase* phases, int nphases, unsigned* counters, const int* epoch, bool pdl, cudaStream_t stream);
+// argument checks shared by every forward entry point (cabi.cu)
+int check_arch();
+int check_forward_args(const char* who, const void* x, int64_t ldx, const void* w, const void* scales, const void* y, int64_t ldy,
+                       int64_t M, int64_t N, int64_t K, int dtype);
 
 // tensor-core (mma.sync) streaming kernel for 2 <= M <= 8 decode rows (gemv_mma.cu)
 bool gemv_mma_supported(int M, int64_t K);
@@ -154,22 +185,6 @@ __device__ __forceinline__ uint4 ldg_stream_128(const void* p)
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
-}
-
-// wait until every rank has published `epoch` in flags[0..world) (written by peers with st.release.sys); all threads of
-// the CTA must call it (contains a __syncthreads)
-__device__ __forceinline__ void p2p_wait_flags(const unsigned* flags, int world, const int* epoch_ptr)
-{
-    if (flags != nullptr) {
-        if (int(threadIdx.x) < world) {
-            const unsigned epoch = unsigned(*epoch_ptr);
-            unsigned v;
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
-            } while (v < epoch);
-        }
-        __syncthreads();
-    }
 }
 
 // programmatic dependent launch (PDL) controls; no-ops when the kernel was launched without the attribute

@@ -277,7 +277,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     // need neither `pos` nor anything the preceding kernel produces.
     load_chunk(0, split);
     load_chunk(1, split + ATT_SPLITS);
-    const int pos = *pos_p;  // written at the end of the previous step
+    pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV; *pos was advanced by the previous
+                             // step's last kernel (transitively complete once the preceding grid is)
+    const int pos = *pos_p;
     float rope_c = 0.f, rope_s = 0.f;
     if (t < ATT_D / 2) {
         rope_c = __half2float(cos_t[int64_t(pos) * (ATT_D / 2) + t]);
@@ -285,7 +287,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     }
     const int new_chunk = pos / ATT_ROWS;
     const bool owns_new = (new_chunk % ATT_SPLITS) == split;
-    pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
 
     // RoPE of q (every CTA) and of the new k (owner CTA); HF rotate_half convention evaluated in fp16
     if (t < ATT_D / 2) {

@@ -8,13 +8,18 @@ This is the caller either side of the hot path (SURVEY.md section 8 "next"), kep
                             (/root/reference/python/eetq/utils/quantizer.py:40-61).  Its ``forward`` is a plain PyTorch
                             implementation used as the numerical reference in tests.
 * ``W8A16LlamaDecoder``  -- takes the quantised model, fuses q|k|v and gate|up row-wise (trivial in the b200 layout:
-                            rows are output features), and runs single-token decode as ONE CUDA graph of native kernels:
-                            per layer 4 streaming GEMVs (RMSNorm / SiLU*up / residual fused into them) and ONE fused
-                            RoPE + KV-append + split-KV attention kernel, chained with programmatic dependent launch so that the weight
-                            stream of kernel i+1 starts while kernel i drains.
-                            With ``world_size > 1`` every linear is column-sharded (rank r owns rows
-                            [r*N/P, (r+1)*N/P) of each fused weight -- a contiguous byte range) and the activations are
-                            all-gathered after each linear.
+                            rows are output features; gate and up rows are INTERLEAVED so the GEMV epilogue can emit
+                            silu(gate) * up directly), and runs single-token decode as ONE CUDA graph of native kernels:
+                            per layer 4 streaming GEMVs (RMSNorm / residual / SiLU*up fused into them) and ONE fused
+                            RoPE + KV-append + attention kernel, then ONE final-norm + lm_head + arg-max kernel, all chained
+                            with programmatic dependent launch.
+
+Multi-GPU (``world_size > 1``): every linear is column-sharded (rank r owns a contiguous block of
+output features = a contiguous byte range of the b200 layout), attention is sharded by head, the lm_head by vocabulary.  The
+vectors every rank needs (attention output, residual stream, MLP activation, arg-max candidates) are exchanged through "LL"
+buffers in symmetric memory: the producing kernel's epilogue stores {2 x fp16, tag} words straight into every rank's copy over
+NVLink and the consuming kernel's prologue polls the words it needs (``exchange="ll"``, default).  ``exchange="nccl"`` keeps plain
+buffers and one ``ncclAllGather`` per sharded linear -- the baseline the fused exchange is measured against.
 
 The reference's own end-to-end path is HF ``generate`` over ``W8A16Linear`` modules
 (/root/reference/examples/models/llama_transformers_example.py:22-90); its attention side
@@ -23,7 +28,6 @@ The reference's own end-to-end path is HF ``generate`` over ``W8A16Linear`` modu
 from __future__ import annotations
 
 import ctypes
-import math
 import os
 from dataclasses import dataclass
 from typing import List, Optional
@@ -34,9 +38,9 @@ import torch.nn.functional as F
 
 from . import _cabi
 from .modules.qlinear import W8A16Linear
-from .ops import w8_a16_gemm_bias
+from .ops import w8_a16_gemm_bias, w8_a16_gemm_residual
 
-__all__ = ["LlamaShape", "LlamaSkeleton", "W8A16LlamaDecoder", "LLAMA2_7B", "LLAMA2_13B"]
+__all__ = ["LlamaShape", "LlamaSkeleton", "W8A16LlamaDecoder", "LLAMA2_7B", "LLAMA2_13B", "shard_plan"]
 
 
 @dataclass
@@ -164,6 +168,27 @@ class LlamaSkeleton(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# sharding plan (pure arithmetic: also exercised by the CPU tests)
+# ---------------------------------------------------------------------------------------------------------------------
+def shard_plan(shape: LlamaShape, rank: int, world: int) -> dict:
+    """Which output features of every (fused) linear rank `rank` of `world` owns, and the exchange indices of a decode step.
+
+    q|k|v: the rows of this rank's heads (q, then k, then v);  o / down: rows [r H/P, (r+1) H/P);  gate|up: the interleaved
+    rows (g_i, u_i) for i in [r I/P, (r+1) I/P);  lm_head: vocabulary rows [r V/P, (r+1) V/P)."""
+    H, I, V, P = shape.hidden, shape.inter, shape.vocab, world
+    if shape.heads % P or H % (64 * P) or (2 * I) % (64 * P) or V % P or shape.head_dim != 128:
+        raise ValueError(f"{shape.name} cannot be sharded {P}-way (heads {shape.heads}, hidden {H}, inter {I}, vocab {V})")
+    hl = shape.heads // P
+    return dict(
+        heads=(rank * hl, (rank + 1) * hl), hidden=(rank * H // P, (rank + 1) * H // P), inter=(rank * I // P, (rank + 1) * I // P),
+        vocab=(rank * V // P, (rank + 1) * V // P),
+        # exchange indices inside one decode step: 0 = embedding, per layer 1..4 = attention out, x + o(...), act, x + down(...);
+        # the last one = arg-max candidates
+        per_step=4 * shape.layers + 2, x_in=lambda l: 4 * l, attn=lambda l: 4 * l + 1, x2=lambda l: 4 * l + 2, act=lambda l: 4 * l + 3,
+        x_out=lambda l: 4 * l + 4, cand=4 * shape.layers + 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # decoder
 # ---------------------------------------------------------------------------------------------------------------------
 def _vp(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
@@ -176,128 +201,114 @@ def _rows(lin: W8A16Linear) -> torch.Tensor:
     return lin.qweight.view(torch.uint8).view(N, K)
 
 
-class _ShardedLinear:
-    """Rows [r*N/P, (r+1)*N/P) of a (possibly fused) quantised linear on this rank."""
+class _Shard:
+    """A contiguous block of rows of a (possibly fused) quantised linear: int8 [K, N_local] (nominal) + scales."""
 
-    def __init__(self, lins: List[W8A16Linear], rank: int, world: int):
-        rows = torch.cat([_rows(l) for l in lins], 0)
-        scales = torch.cat([l.weight_scales for l in lins], 0)
-        N, K = rows.shape
-        assert N % (64 * world) == 0, f"N={N} cannot be column-sharded {world}-way in multiples of 64"
-        self.N, self.K = N, K
-        self.n_local = N // world
-        self.n_begin = rank * self.n_local
-        sl = slice(self.n_begin, self.n_begin + self.n_local)
-        self.w = rows[sl].contiguous().view(torch.int8).view(K, self.n_local)  # nominal [K, N_local] like the reference
-        self.scales = scales[sl].contiguous()
+    def __init__(self, rows: torch.Tensor, scales: torch.Tensor):
+        self.N, self.K = rows.shape
+        self.w = rows.contiguous().view(torch.int8).view(self.K, self.N)  # nominal [K, N_local] like the reference
+        self.scales = scales.contiguous()
 
 
 class W8A16LlamaDecoder:
     def __init__(self, model: nn.Module, shape: LlamaShape, max_ctx: int = 1280, pdl: bool = True, rank: int = 0, world_size: int = 1,
-                 group=None, allgather: Optional[str] = None, chain: Optional[bool] = None):
+                 group=None, exchange: Optional[str] = None):
         self.shape, self.max_ctx, self.pdl = shape, max_ctx, bool(pdl)
         self.rank, self.world, self.group = rank, world_size, group
-        # "p2p": all-gather fused into the GEMV epilogue over NVLink peer memory; "nccl": one ncclAllGather per linear
-        # (default: NCCL measured 388 tok/s vs 344 for the first p2p protocol at N=2, DESIGN.md section 6)
-        self.allgather = (allgather or os.environ.get("EETQ_B200_ALLGATHER", "nccl")) if world_size > 1 else "none"
+        self.exchange = (exchange or os.environ.get("EETQ_B200_EXCHANGE", "ll")) if world_size > 1 else "none"
+        assert self.exchange in ("none", "ll", "nccl")
+        plan = self.plan = shard_plan(shape, rank, world_size)
         m = model.model
-        dev = m.embed_tokens.weight.device
-        self.device = dev
+        dev = self.device = m.embed_tokens.weight.device
         dt = torch.float16
+        H, I, L, D = shape.hidden, shape.inter, shape.layers, shape.head_dim
+        h0, h1 = plan["heads"]
+        n0, n1 = plan["hidden"]
+        i0, i1 = plan["inter"]
+        v0, v1 = plan["vocab"]
+        self.Hl, self.Il, self.Vl = (h1 - h0) * D, i1 - i0, v1 - v0
         self.embed = m.embed_tokens.weight.detach()
-        self.lm_head_w = model.lm_head.weight.detach()  # fp16 [V, H], not quantised (quantizer.py:40 excludes lm_head)
+        self.lm_head_w = model.lm_head.weight.detach()[v0:v1].contiguous()  # fp16 [V/P, H], not quantised (quantizer.py:40)
         self.norm_w = m.norm.weight.detach()
         self.layers = []
         for layer in m.layers:
             a, p = layer.self_attn, layer.mlp
             for lin in (a.q_proj, a.k_proj, a.v_proj, a.o_proj, p.gate_proj, p.up_proj, p.down_proj):
                 assert isinstance(lin, W8A16Linear), "run eet_quantize(model) first"
+            hs = slice(h0 * D, h1 * D)
+            qkv_rows = torch.cat([_rows(a.q_proj)[hs], _rows(a.k_proj)[hs], _rows(a.v_proj)[hs]], 0)
+            qkv_scales = torch.cat([a.q_proj.weight_scales[hs], a.k_proj.weight_scales[hs], a.v_proj.weight_scales[hs]], 0)
+            gu_rows = torch.stack([_rows(p.gate_proj)[i0:i1], _rows(p.up_proj)[i0:i1]], 1).reshape(2 * (i1 - i0), H)
+            gu_scales = torch.stack([p.gate_proj.weight_scales[i0:i1], p.up_proj.weight_scales[i0:i1]], 1).reshape(-1)
             self.layers.append(dict(
-                qkv=_ShardedLinear([a.q_proj, a.k_proj, a.v_proj], rank, world_size),
-                o=_ShardedLinear([a.o_proj], rank, world_size),
-                gu=_ShardedLinear([p.gate_proj, p.up_proj], rank, world_size),
-                down=_ShardedLinear([p.down_proj], rank, world_size),
+                qkv=_Shard(qkv_rows, qkv_scales), o=_Shard(_rows(a.o_proj)[n0:n1], a.o_proj.weight_scales[n0:n1]),
+                gu=_Shard(gu_rows, gu_scales), down=_Shard(_rows(p.down_proj)[n0:n1], p.down_proj.weight_scales[n0:n1]),
                 ln1=layer.input_layernorm.weight.detach(), ln2=layer.post_attention_layernorm.weight.detach()))
-        H, I, L = shape.hidden, shape.inter, shape.layers
         self.cos, self.sin = rope_tables(shape, max_ctx, dev, dt)
-        # KV cache, head-major: [layer][head][max_ctx][head_dim] (each attention CTA streams one contiguous block)
-        self.kcache = torch.zeros(L, shape.heads, max_ctx, shape.head_dim, dtype=dt, device=dev)
-        self.vcache = torch.zeros(L, shape.heads, max_ctx, shape.head_dim, dtype=dt, device=dev)
-        # decode-step buffers (device resident; the graph reads/writes these)
+        # KV cache of this rank's heads, head-major: [layer][head][max_ctx][head_dim]
+        self.kcache = torch.zeros(L, h1 - h0, max_ctx, D, dtype=dt, device=dev)
+        self.vcache = torch.zeros(L, h1 - h0, max_ctx, D, dtype=dt, device=dev)
+        # decode-step state (device resident; the graph reads/writes these)
         self.token = torch.zeros(1, dtype=torch.int64, device=dev)
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)   # strictly increasing step counter (p2p flags)
-        self._p2p = None
-        if self.allgather == "p2p":
-            try:
-                self._setup_p2p(H, I, L, dt, dev)
-            except Exception as e:  # symmetric memory unavailable -> NCCL all-gather (still a GPU path, never a CPU one)
-                if rank == 0:
-                    print(f"[eetq_b200] p2p all-gather unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
-                self.allgather, self._p2p = "nccl", None
-        if self._p2p is None:
-            self.x = torch.zeros(H, dtype=dt, device=dev)
-            self.x2 = torch.zeros(H, dtype=dt, device=dev)
-            self.qkv = torch.zeros(3 * H, dtype=dt, device=dev)
-            self.gu = torch.zeros(2 * I, dtype=dt, device=dev)
-        self.attn = torch.zeros(H, dtype=dt, device=dev)
-        # single GPU: o_proj -> gate|up -> down -> next q|k|v run as ONE chained launch per layer (grid barriers inside)
-        if chain is None:
-            chain = os.environ.get("EETQ_B200_CHAIN", "0") == "1"   # measured slower than PDL-chained launches (DESIGN.md section 7)
-        self.chain = bool(chain) and world_size == 1
-        self.chain_counters = torch.zeros(L, 4, dtype=torch.int32, device=dev)
-        # the q|k|v GEMV of a layer prefetches that layer's KV cache rows into L2 for the attention kernel that follows
-        # (measured slower, 551 vs 563 tok/s: off by default, DESIGN.md section 7)
-        self.kv_prefetch = os.environ.get("EETQ_B200_KV_PREFETCH", "0") == "1"
-        self.xn = torch.zeros(1, H, dtype=dt, device=dev)
+        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)  # LL tag base, advanced by the lm_head kernel
+        self.qkv = torch.zeros(3 * self.Hl, dtype=dt, device=dev)
         self.logits = torch.zeros(1, shape.vocab, dtype=dt, device=dev)
         self._L = _cabi.lib()
-        splits = int(self._L.eetq_b200_decode_attention_splits(max_ctx))
-        self.partial = torch.zeros(shape.heads * splits * (shape.head_dim + 2), dtype=torch.float32, device=dev)
-        self.tickets = torch.zeros(shape.heads, dtype=torch.int32, device=dev)
+        self.lm_scratch = torch.zeros(int(self._L.eetq_b200_lm_head_scratch_bytes()), dtype=torch.uint8, device=dev)
+        self._ll = None
+        if self.exchange == "ll":
+            try:
+                self._setup_ll(H, I, dev)
+            except Exception as e:  # symmetric memory unavailable -> NCCL all-gather (still a GPU path, never a CPU one)
+                if rank == 0:
+                    print(f"[eetq_b200] LL exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather", flush=True)
+                self.exchange = "nccl"
+        if self._ll is None:
+            self.x = torch.zeros(H, dtype=dt, device=dev)
+            self.x2 = torch.zeros(H, dtype=dt, device=dev)
+            self.attn = torch.zeros(H, dtype=dt, device=dev)
+            self.act = torch.zeros(I, dtype=dt, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
 
-    # ------------------------------------------------------------------------------------------------- p2p all-gather
-    def _setup_p2p(self, H, I, L, dt, dev):
-        """Activation buffers + flags in ONE symmetric-memory arena mapped into every rank (NVLink peer pointers)."""
+    # ------------------------------------------------------------------------------------------------- LL exchange buffers
+    def _setup_ll(self, H, I, dev):
+        """LL buffers (8-byte words {2 x fp16, tag}) in ONE symmetric-memory arena mapped into every rank."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
         def rnd(n):
             return (n + 255) // 256 * 256
 
-        nslot = 4 * L
-        sizes = [("x", H * 2), ("x2", H * 2), ("qkv", 3 * H * 2), ("gu", 2 * I * 2), ("flags", nslot * 8 * 4)]
+        sizes = [("x", H * 4), ("x2", H * 4), ("attn", H * 4), ("act", I * 4), ("cand", 2 * 8 * 8)]
         offs, total = {}, 0
         for name, nb in sizes:
             offs[name] = total
             total += rnd(nb)
         arena = symm_mem.empty(total, dtype=torch.uint8, device=dev)
-        arena.zero_()
+        arena.zero_()  # tag 0 is never a valid tag
         group = self.group if self.group is not None else dist.group.WORLD
         hdl = symm_mem.rendezvous(arena, group)
         bases = [int(b) for b in hdl.buffer_ptrs]
         assert len(bases) == self.world
-        view = lambda name, nb, dtype: arena[offs[name]:offs[name] + nb].view(dtype)
-        self.x, self.x2 = view("x", H * 2, dt), view("x2", H * 2, dt)
-        self.qkv, self.gu = view("qkv", 3 * H * 2, dt), view("gu", 2 * I * 2, dt)
-        flags = view("flags", nslot * 8 * 4, torch.int32)
-        self._p2p = dict(arena=arena, hdl=hdl, bases=bases, offs=offs, flags=flags, nslot=nslot,
-                         ticket=torch.zeros(1, dtype=torch.int32, device=dev), slot=0)
+        self._ll = dict(arena=arena, hdl=hdl, bases=bases, offs=offs)
         torch.cuda.synchronize(dev)
-        dist.barrier(group=group)   # every rank's flags are zero before anybody signals
+        dist.barrier(group=group)  # every rank's buffers are zero before anybody pushes
 
-    def _p2p_args(self, y_full: torch.Tensor, lin, slot: int):
-        """ctypes arrays of peer pointers for output buffer `y_full` (a view into the arena) and flag slot `slot`."""
-        p = self._p2p
-        arena_base = p["arena"].data_ptr()
-        y_off = y_full.data_ptr() - arena_base + lin.n_begin * 2            # this rank's first row inside the buffer
-        f_off = p["offs"]["flags"] + (slot * 8) * 4
-        peer_y = (ctypes.c_uint64 * 8)(*[b + y_off for b in p["bases"]] + [0] * (8 - self.world))
-        peer_f = (ctypes.c_uint64 * 8)(*[b + f_off + self.rank * 4 for b in p["bases"]] + [0] * (8 - self.world))
-        local_flags = ctypes.c_void_p(arena_base + f_off)
-        return peer_y, peer_f, local_flags
+    def _ll_local(self, name: str) -> int:
+        return self._ll["arena"].data_ptr() + self._ll["offs"][name]
+
+    def _tag(self, index: int):
+        return _cabi.LL(self.step_ctr.data_ptr(), self.plan["per_step"], index)
+
+    def _push(self, name: str, elem_off: int, index: int):
+        ll = self._ll
+        peers = (ctypes.c_uint64 * 8)(*[b + ll["offs"][name] for b in ll["bases"]] + [0] * (8 - self.world))
+        p = _cabi.LLPush(self.world, ctypes.cast(peers, ctypes.POINTER(ctypes.c_uint64)), self._ll_local(name), elem_off,
+                         self.step_ctr.data_ptr(), self.plan["per_step"], index)
+        p._keep = peers  # keep the host array alive as long as the struct
+        return p
 
     # ------------------------------------------------------------------------------------------------- construction
     @classmethod
@@ -308,126 +319,140 @@ class W8A16LlamaDecoder:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _flags_ptr(self, slot):
-        """Address of this rank's flags[slot][0..world) inside the symmetric arena (None -> NULL)."""
-        if slot is None or self._p2p is None:
-            return ctypes.c_void_p(0)
-        p = self._p2p
-        return ctypes.c_void_p(p["arena"].data_ptr() + p["offs"]["flags"] + (slot * 8) * 4)
+    def _all_gather(self, full: torch.Tensor, part: torch.Tensor):
+        import torch.distributed as dist
 
-    def _gemv(self, x, ldx, lin: _ShardedLinear, y_full, *, norm_w=None, xmode=0, residual_full=None, wait_slot=None, kv_layer=None):
-        """y_full[n_begin : n_begin + n_local] = fused GEMV over this rank's rows; then all-gather if sharded.
-        p2p mode: returns the flag slot this call publishes; `wait_slot` is the slot of the call that produced `x`."""
-        off = lin.n_begin
-        y = y_full[off:off + lin.n_local]
-        res = None if residual_full is None else residual_full[off:off + lin.n_local]
-        if self._p2p is not None:
-            p = self._p2p
-            slot = p["slot"] % p["nslot"]
-            p["slot"] += 1
-            peer_y, peer_f, local_flags = self._p2p_args(y_full, lin, slot)
-            rc = self._L.eetq_b200_w8a16_gemv_fused_p2p(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), _vp(norm_w), float(self.shape.eps), xmode,
-                                                        _vp(res), lin.N, 1, lin.n_local, lin.K, _cabi.F16, self.world, peer_y, peer_f,
-                                                        local_flags, self._flags_ptr(wait_slot), _vp(p["ticket"]), _vp(self.epoch), lin.N,
-                                                        1 if self.pdl else 0, self._stream())
-            _cabi.check(rc, "eetq_b200_w8a16_gemv_fused_p2p")
-            return slot
-        if kv_layer is not None and self.kv_prefetch and self.world == 1:
-            rc = self._L.eetq_b200_w8a16_gemv_fused_kvprefetch(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), _vp(norm_w), float(self.shape.eps),
-                                                               xmode, _vp(res), lin.N, _vp(y), lin.N, 1, lin.n_local, lin.K, _cabi.F16,
-                                                               _vp(self.kcache[kv_layer]), _vp(self.vcache[kv_layer]), _vp(self.pos),
-                                                               self.shape.heads, self.max_ctx, 1 if self.pdl else 0, self._stream())
-            _cabi.check(rc, "eetq_b200_w8a16_gemv_fused_kvprefetch")
-            return None
-        rc = self._L.eetq_b200_w8a16_gemv_fused(_vp(x), ldx, _vp(lin.w), _vp(lin.scales), None, _vp(norm_w), float(self.shape.eps),
-                                                xmode, _vp(res), lin.N, _vp(y), lin.N, 1, lin.n_local, lin.K, _cabi.F16,
-                                                1 if self.pdl else 0, self._stream())
+        dist.all_gather_into_tensor(full, part, group=self.group)
+
+    def _gemv(self, x, ldx, lin: _Shard, y, *, norm_w=None, xmode=0, epi=0, residual=None, x_tag=None, res_tag=None, res_off=0, push=None):
+        """One fused decode GEMV over this rank's rows.  x / residual: tensors (plain) or raw LL addresses (int) with their tags."""
+        o = _cabi.GemvOpts()
+        o.norm_weight = 0 if norm_w is None else norm_w.data_ptr()
+        o.eps, o.xmode, o.epi = float(self.shape.eps), xmode, epi
+        o.residual = 0 if residual is None else (residual if isinstance(residual, int) else residual.data_ptr())
+        o.ldr = lin.N
+        o.x_ll = ctypes.pointer(x_tag) if x_tag is not None else None
+        o.residual_ll = ctypes.pointer(res_tag) if res_tag is not None else None
+        o.residual_off = res_off
+        o.push = ctypes.pointer(push) if push is not None else None
+        xp = ctypes.c_void_p(x if isinstance(x, int) else x.data_ptr())
+        rc = self._L.eetq_b200_w8a16_gemv_fused(xp, ldx, _vp(lin.w), _vp(lin.scales), None, _vp(y), lin.N, 1, lin.N, lin.K, _cabi.F16,
+                                                ctypes.byref(o), 1 if self.pdl else 0, self._stream())
         _cabi.check(rc, "eetq_b200_w8a16_gemv_fused")
-        if self.world > 1:
-            import torch.distributed as dist
-
-            dist.all_gather_into_tensor(y_full[:lin.N], y, group=self.group)
 
     # ------------------------------------------------------------------------------------------------- one decode step
     def _enqueue_step(self):
         """Enqueue one token's worth of kernels on the current stream (captured once into a CUDA graph)."""
-        s, L, pdl = self.shape, self._L, 1 if self.pdl else 0
+        s, L, pdl, plan = self.shape, self._L, 1 if self.pdl else 0, self.plan
         H, I, D = s.hidden, s.inter, s.head_dim
         st = self._stream
-        if self._p2p is not None:
-            self._p2p["slot"] = 0
-            self.epoch.add_(1)   # one epoch per decode step; flags[slot] only ever increase
-        _cabi.check(L.eetq_b200_decode_embed(_vp(self.embed), _vp(self.token), _vp(self.x), H, pdl, st()), "decode_embed")
-        def attention(li, wait_slot=None):
-            _cabi.check(L.eetq_b200_decode_attention_p2p(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
-                                                         _vp(self.vcache[li]), _vp(self.partial), _vp(self.tickets), _vp(self.attn), H, D,
-                                                         self.max_ctx, self._flags_ptr(wait_slot), self.world, _vp(self.epoch), pdl, st()),
-                        "decode_attention")
+        n0 = plan["hidden"][0]
+        i0 = plan["inter"][0]
+        ll = self._ll is not None
+        nccl = self.exchange == "nccl"
 
-        if self.chain:
-            nl = len(self.layers)
-            self.epoch.add_(1)
-            self._gemv(self.x, H, self.layers[0]["qkv"], self.qkv, norm_w=self.layers[0]["ln1"], xmode=1)
-            for li, w in enumerate(self.layers):
-                attention(li)
-                # x2 = x + o_proj(attn); gu = gate|up(norm(x2)); x = x2 + down(silu(gate)*up); qkv = q|k|v(norm(x)) of the next layer
-                phases = [
-                    (self.attn, H, w["o"], self.x2, None, self.x, 0),
-                    (self.x2, H, w["gu"], self.gu, w["ln2"], None, 1),
-                    (self.gu, 2 * I, w["down"], self.x, None, self.x2, 2),
-                ]
-                if li + 1 < nl:
-                    nxt = self.layers[li + 1]
-                    phases.append((self.x, H, nxt["qkv"], self.qkv, nxt["ln1"], None, 1))
-                arr = (_cabi.GemvPhase * len(phases))()
-                for i, (xin, ldx, lin, y, nw, res, xmode) in enumerate(phases):
-                    arr[i] = _cabi.GemvPhase(xin.data_ptr(), ldx, lin.w.data_ptr(), lin.scales.data_ptr(), y.data_ptr(), lin.N, lin.K,
-                                             0 if nw is None else nw.data_ptr(), 0 if res is None else res.data_ptr(), float(s.eps), xmode)
-                _cabi.check(L.eetq_b200_w8a16_gemv_chain(ctypes.byref(arr), len(phases), _vp(self.chain_counters[li]), _vp(self.epoch),
-                                                          pdl, st()), "eetq_b200_w8a16_gemv_chain")
+        if ll:
+            xt = self._tag(plan["x_in"](0))
+            _cabi.check(L.eetq_b200_decode_embed(_vp(self.embed), _vp(self.token), ctypes.c_void_p(self._ll_local("x")), H, ctypes.byref(xt), pdl,
+                                                 st()), "decode_embed")
         else:
-            # p2p mode: each call returns the flag slot it publishes; the kernel that consumes its output waits on that slot
-            s_x = None   # slot of the call that produced self.x (None: produced locally by the embedding gather)
-            for li, w in enumerate(self.layers):
-                s_qkv = self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1, wait_slot=s_x, kv_layer=li)
-                attention(li, wait_slot=s_qkv)
-                # x2 = x + o_proj(attn); x = x2 + down(silu(gate) * up)   (ping-pong so no kernel reads what it writes)
-                s_o = self._gemv(self.attn, H, w["o"], self.x2, residual_full=self.x)       # attn is local, x already waited for
-                s_gu = self._gemv(self.x2, H, w["gu"], self.gu, norm_w=w["ln2"], xmode=1, wait_slot=s_o)
-                s_x = self._gemv(self.gu, 2 * I, w["down"], self.x, xmode=2, residual_full=self.x2, wait_slot=s_gu)
-        last_slot = s_x if (self._p2p is not None and not self.chain) else None
-        _cabi.check(L.eetq_b200_decode_rmsnorm_p2p(_vp(self.x), _vp(self.norm_w), _vp(self.xn), 1, H, float(s.eps), self._flags_ptr(last_slot),
-                                                   self.world, _vp(self.epoch), pdl, st()), "decode_rmsnorm")
-        torch.matmul(self.xn, self.lm_head_w.t(), out=self.logits)       # fp16 lm_head (library GEMV; not quantised)
-        self.token.copy_(torch.argmax(self.logits, dim=-1))               # greedy
-        self.pos.add_(1)
+            _cabi.check(L.eetq_b200_decode_embed(_vp(self.embed), _vp(self.token), _vp(self.x), H, None, pdl, st()), "decode_embed")
+
+        for li, w in enumerate(self.layers):
+            if ll:
+                x_in, x_tag = self._ll_local("x"), self._tag(plan["x_in"](li))
+                # q|k|v of this rank's heads (plain, local)
+                self._gemv(x_in, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1, x_tag=x_tag)
+                push = self._push("attn", plan["heads"][0] * D, plan["attn"](li))
+                _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
+                                                         _vp(self.vcache[li]), None, self.Hl, D, self.max_ctx, ctypes.byref(push), pdl, st()),
+                            "decode_attention")
+                # x2 = x + o_proj(attn)
+                self._gemv(self._ll_local("attn"), H, w["o"], None, x_tag=self._tag(plan["attn"](li)), residual=x_in, res_tag=x_tag, res_off=n0,
+                           push=self._push("x2", n0, plan["x2"](li)))
+                # act = silu(gate(norm(x2))) * up(norm(x2))
+                x2_tag = self._tag(plan["x2"](li))
+                self._gemv(self._ll_local("x2"), H, w["gu"], None, norm_w=w["ln2"], xmode=1, epi=1, x_tag=x2_tag,
+                           push=self._push("act", i0, plan["act"](li)))
+                # x = x2 + down(act)
+                self._gemv(self._ll_local("act"), I, w["down"], None, x_tag=self._tag(plan["act"](li)), residual=self._ll_local("x2"),
+                           res_tag=x2_tag, res_off=n0, push=self._push("x", n0, plan["x_out"](li)))
+            else:
+                self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1)
+                attn_out = self.attn[n0:n0 + self.Hl] if nccl else self.attn
+                _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
+                                                         _vp(self.vcache[li]), _vp(attn_out), self.Hl, D, self.max_ctx, None, pdl, st()),
+                            "decode_attention")
+                if nccl:
+                    self._all_gather(self.attn, attn_out)
+                sl = slice(n0, n0 + w["o"].N)
+                self._gemv(self.attn, H, w["o"], self.x2[sl], residual=self.x[sl])
+                if nccl:
+                    self._all_gather(self.x2, self.x2[sl])
+                al = slice(i0, i0 + self.Il)
+                self._gemv(self.x2, H, w["gu"], self.act[al], norm_w=w["ln2"], xmode=1, epi=1)
+                if nccl:
+                    self._all_gather(self.act, self.act[al])
+                self._gemv(self.act, I, w["down"], self.x[sl], residual=self.x2[sl])
+                if nccl:
+                    self._all_gather(self.x, self.x[sl])
+
+        v0 = plan["vocab"][0]
+        if ll:
+            xt = self._tag(plan["x_out"](len(self.layers) - 1))
+            cand = self._push("cand", 0, plan["cand"])
+            rc = L.eetq_b200_lm_head_argmax(ctypes.c_void_p(self._ll_local("x")), ctypes.byref(xt), _vp(self.norm_w), float(s.eps),
+                                            _vp(self.lm_head_w), self.Vl, H, v0, _vp(self.logits), _vp(self.lm_scratch), _vp(self.token),
+                                            _vp(self.pos), _vp(self.step_ctr), ctypes.byref(cand), self.rank, pdl, st())
+            _cabi.check(rc, "lm_head_argmax")
+        else:
+            rc = L.eetq_b200_lm_head_argmax(_vp(self.x), None, _vp(self.norm_w), float(s.eps), _vp(self.lm_head_w), self.Vl, H, v0,
+                                            _vp(self.logits), _vp(self.lm_scratch), _vp(self.token), _vp(self.pos), _vp(self.step_ctr), None,
+                                            self.rank, pdl, st())
+            _cabi.check(rc, "lm_head_argmax")
+            if nccl:
+                # baseline path: gather the logits slices and pick the winner with framework ops
+                self._all_gather(self.logits.view(-1), self.logits.view(-1)[v0:v0 + self.Vl])
+                self.token.copy_(torch.argmax(self.logits, dim=-1))
 
     def capture(self):
-        """Warm up (lazy module loads, cuBLAS handles) and capture the decode step into a CUDA graph."""
-        saved_pos, saved_tok = self.pos.clone(), self.token.clone()
+        """Warm up (lazy module loads) and capture the decode step into a CUDA graph."""
+        saved = (self.pos.clone(), self.token.clone())
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(2):
+                self._check_room()
                 self._enqueue_step()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
-        self.pos.copy_(saved_pos)
-        self.token.copy_(saved_tok)
+        self.pos.copy_(saved[0])
+        self.token.copy_(saved[1])
         before = _cabi.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._enqueue_step()
         self.launches_per_step = _cabi.launch_count() - before
         torch.cuda.synchronize(self.device)
-        self.pos.copy_(saved_pos)
-        self.token.copy_(saved_tok)
+        self.pos.copy_(saved[0])
+        self.token.copy_(saved[1])
+        self._host_pos = int(self.pos.item())
+
+    def _check_room(self):
+        """The attention kernel appends at row *pos: refuse to step past the end of the KV cache (host-tracked position)."""
+        hp = getattr(self, "_host_pos", None)
+        if hp is None:
+            hp = self._host_pos = int(self.pos.item())
+        if hp + 1 > self.max_ctx:
+            raise RuntimeError(f"KV cache is full: position {hp} + 1 > max_ctx {self.max_ctx}")
 
     def step(self):
-        """Advance one token entirely on the device (token/pos buffers are updated by the graph)."""
+        """Advance one token entirely on the device (token / position / step counter are updated by the graph)."""
         if self.graph is None:
             self.capture()
+        self._check_room()
         self.graph.replay()
+        self._host_pos += 1
 
     def step_host(self, token_host: torch.Tensor, out_host: torch.Tensor):
         """Public end-to-end call: token id in PINNED host memory -> next token id in pinned host memory
@@ -441,47 +466,69 @@ class W8A16LlamaDecoder:
     # ------------------------------------------------------------------------------------------------- prefill
     @torch.no_grad()
     def prefill(self, tokens: torch.Tensor) -> torch.Tensor:
-        """Process a prompt [T] with the batched (tcgen05) kernels, fill the KV cache, return the first new token."""
-        s = self.shape
-        T, H = tokens.shape[0], s.hidden
-        assert T < self.max_ctx
-        x = self.embed[tokens]
-        cos, sin = self.cos[:T], self.sin[:T]
-
-        def lin(inp, l: _ShardedLinear):
-            y = w8_a16_gemm_bias(inp, l.w, l.scales, None)
-            if self.world > 1:
-                import torch.distributed as dist
-
-                parts = [torch.empty_like(y) for _ in range(self.world)]
-                dist.all_gather(parts, y, group=self.group)
-                y = torch.cat(parts, -1)
-            return y
+        """Process a prompt [T] with the batched (tcgen05) kernels, fill the KV cache, return the first new token.
+        Native kernels: w8a16 GEMMs (residual adds fused), RMSNorm, RoPE + KV-cache write, SiLU*up, final norm + lm_head +
+        arg-max; causal attention over the prompt uses the framework's SDPA (attention is outside the w8a16 hot path)."""
+        s, L, plan = self.shape, self._L, self.plan
+        T, H, D = tokens.shape[0], s.hidden, s.head_dim
+        assert 0 < T < self.max_ctx
+        dev, dt = self.device, torch.float16
+        st = self._stream()
+        hl = plan["heads"][1] - plan["heads"][0]
+        n0, n1 = plan["hidden"]
+        x = self.embed[tokens].contiguous()
 
         def rms(v, w):
-            vf = v.float()
-            return w * (vf * torch.rsqrt(vf.pow(2).mean(-1, keepdim=True) + s.eps)).to(v.dtype)
+            out = torch.empty_like(v)
+            _cabi.check(L.eetq_b200_rmsnorm(_vp(v), v.stride(0), _vp(w), _vp(out), out.stride(0), v.shape[0], H, float(s.eps), 0, st), "rmsnorm")
+            return out
+
+        def gather_cols(part):
+            """[T, n_local] on every rank -> [T, n_local * P] (rank-major feature order)."""
+            if self.world == 1:
+                return part
+            import torch.distributed as dist
+
+            buf = torch.empty(self.world, *part.shape, dtype=part.dtype, device=dev)
+            dist.all_gather_into_tensor(buf, part.contiguous(), group=self.group)
+            return buf.permute(1, 0, 2).reshape(part.shape[0], -1).contiguous()
 
         for li, w in enumerate(self.layers):
-            qkv = lin(rms(x, w["ln1"]), w["qkv"])
-            q = apply_rope(qkv[:, :H].reshape(T, s.heads, s.head_dim), cos, sin)
-            k = apply_rope(qkv[:, H:2 * H].reshape(T, s.heads, s.head_dim), cos, sin)
-            v = qkv[:, 2 * H:].reshape(T, s.heads, s.head_dim)
-            self.kcache[li, :, :T] = k.transpose(0, 1)
-            self.vcache[li, :, :T] = v.transpose(0, 1)
-            o = F.scaled_dot_product_attention(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), is_causal=True)
-            x = x + lin(o.transpose(0, 1).reshape(T, H), w["o"])
-            gu = lin(rms(x, w["ln2"]), w["gu"])
-            x = x + lin(F.silu(gu[:, :s.inter]) * gu[:, s.inter:], w["down"])
-        logits = torch.matmul(rms(x[-1:], self.norm_w), self.lm_head_w.t())
-        self.token.copy_(torch.argmax(logits, dim=-1))
-        self.pos.fill_(T)
+            qkv = w8_a16_gemm_bias(rms(x, w["ln1"]), w["qkv"].w, w["qkv"].scales, None)          # [T, 3 Hl]
+            _cabi.check(L.eetq_b200_prefill_rope_kv(_vp(qkv), qkv.stride(0), _vp(self.cos), _vp(self.sin), _vp(self.kcache[li]),
+                                                    _vp(self.vcache[li]), T, hl, D, self.max_ctx, 0, st), "prefill_rope_kv")
+            q = qkv[:, :self.Hl].view(T, hl, D).transpose(0, 1)
+            k = self.kcache[li, :, :T]
+            v = self.vcache[li, :, :T]
+            o = F.scaled_dot_product_attention(q, k, v, is_causal=True)                             # [hl, T, D]
+            attn = gather_cols(o.transpose(0, 1).reshape(T, self.Hl))
+            x2 = gather_cols(w8_a16_gemm_residual(attn, w["o"].w, w["o"].scales, x[:, n0:n1]))
+            gu = w8_a16_gemm_bias(rms(x2, w["ln2"]), w["gu"].w, w["gu"].scales, None)             # [T, 2 Il] interleaved (g, u)
+            act = torch.empty(T, self.Il, dtype=dt, device=dev)
+            _cabi.check(L.eetq_b200_silu_mul(_vp(gu), gu.stride(0), _vp(act), act.stride(0), T, self.Il, 1, st), "silu_mul")
+            act = gather_cols(act)
+            x = gather_cols(w8_a16_gemm_residual(act, w["down"].w, w["down"].scales, x2[:, n0:n1]))
+        # first new token: final norm + lm_head + arg-max on the last row (the kernel advances pos and the step counter)
+        last = x[-1].contiguous()
+        self.pos.fill_(T - 1)
+        cand = self._push("cand", 0, plan["cand"]) if self._ll is not None else None
+        rc = L.eetq_b200_lm_head_argmax(_vp(last), None, _vp(self.norm_w), float(s.eps), _vp(self.lm_head_w), self.Vl, H, plan["vocab"][0],
+                                        _vp(self.logits), _vp(self.lm_scratch), _vp(self.token), _vp(self.pos), _vp(self.step_ctr),
+                                        ctypes.byref(cand) if cand is not None else None, self.rank, 0, st)
+        _cabi.check(rc, "lm_head_argmax")
+        if self.exchange == "nccl":
+            v0 = plan["vocab"][0]
+            self._all_gather(self.logits.view(-1), self.logits.view(-1)[v0:v0 + self.Vl])
+            self.token.copy_(torch.argmax(self.logits, dim=-1))
+        self._host_pos = T
         return self.token.clone()
 
     def set_context(self, ctx_len: int, token: int = 1):
         """Pretend `ctx_len` tokens are already cached (cache content stays as is) -- for benchmarks/tests."""
+        assert 0 <= ctx_len < self.max_ctx
         self.pos.fill_(ctx_len)
         self.token.fill_(token)
+        self._host_pos = ctx_len
 
     @torch.no_grad()
     def generate(self, prompt: torch.Tensor, max_new_tokens: int) -> List[int]:
@@ -494,4 +541,7 @@ class W8A16LlamaDecoder:
     # ------------------------------------------------------------------------------------------------- accounting
     def weight_bytes_per_token(self) -> int:
         """int8 weight bytes THIS rank streams per decoded token (quantised linears only)."""
-        return sum(l.n_local * l.K for w in self.layers for l in (w["qkv"], w["o"], w["gu"], w["down"]))
+        return sum(l.N * l.K for w in self.layers for l in (w["qkv"], w["o"], w["gu"], w["down"]))
+
+    def lm_head_bytes_per_token(self) -> int:
+        return self.lm_head_w.numel() * 2

@@ -8,6 +8,14 @@ State-dict compatibility (so checkpoints and HF integrations line up key for key
   W8A16Linear : ``qweight`` int8 [in, out] (kernel-layout bytes), ``weight_scales`` [out], ``bias`` [out] or absent
   EetqLinear  : ``weight``  int8 [in, out], ``weight_scales`` registered late through ``register_scale``, ``bias``
 
+Checkpoint layout marker.  The int8 bytes of ``qweight`` / ``weight`` are in the b200 layout here but in the sm80 interleaved
+layout in checkpoints written by reference EETQ / Hugging Face (python/eetq/models/base.py:108-146) -- same key, shape and
+dtype, different meaning.  Every module therefore carries a persistent ``weight_layout`` buffer (value ``B200_LAYOUT``) that is
+saved with it; ``load_state_dict`` converts the weight on the GPU (closed form of cutlass_preprocessors.cc:497-534) when the
+marker is absent, i.e. when the state dict comes from a reference build, and refuses unknown marker values.  Reference
+builds in turn reject b200 checkpoints (unexpected key) instead of silently mis-reading them; ``export_reference_state_dict``
+writes the reference's bytes for them.
+
 What differs from the reference: weights are quantised on the layer's own device by the GPU quantiser (the reference
 round-trips through ``.cpu()``, :16), the bias add is fused into the kernel epilogue (the reference issues a second torch
 kernel, :61 and :77), bf16 modules are accepted.  ``W8A16LoraLinear`` (:127-186) never calls ``nn.Module.__init__`` in the
@@ -21,9 +29,60 @@ import torch
 from torch import nn
 from torch.autograd import Function
 
-from ..ops import preprocess_weights, quant_weights, w8_a16_gemm, w8_a16_gemm_bias
+from ..ops import convert_ref_checkpoint_weight, preprocess_weights, quant_weights, to_ref_checkpoint_weight, w8_a16_gemm, w8_a16_gemm_bias
 
-__all__ = ["quantize_and_preprocess_weights", "W8A16Linear", "EetqLinearMMFunction", "EetqLinear"]
+__all__ = ["quantize_and_preprocess_weights", "W8A16Linear", "EetqLinearMMFunction", "EetqLinear", "B200_LAYOUT",
+           "export_reference_state_dict"]
+
+B200_LAYOUT = 200   # value of the ``weight_layout`` marker: bytes are output-feature-major, biased
+_LAYOUT_KEY = "weight_layout"
+
+
+class _LayoutAwareMixin:
+    """``load_state_dict`` support shared by W8A16Linear / EetqLinear: convert reference-layout weights, check the marker."""
+
+    _weight_key = "qweight"
+
+    def _register_layout_marker(self, device) -> None:
+        self.register_buffer(_LAYOUT_KEY, torch.tensor([B200_LAYOUT], dtype=torch.int32, device=device))
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        wkey, lkey = prefix + self._weight_key, prefix + _LAYOUT_KEY
+        if wkey in state_dict:
+            if lkey not in state_dict:
+                # written by a reference build: sm80 interleaved bytes -> b200 layout (a GPU kernel; results return to the
+                # tensor's own device)
+                w = state_dict[wkey]
+                if w.dtype != torch.int8 or w.dim() != 2:
+                    error_msgs.append(f"{wkey}: expected a 2-D int8 tensor, got {tuple(w.shape)} {w.dtype}")
+                else:
+                    if not torch.cuda.is_available():
+                        raise RuntimeError(f"{wkey} is in the reference layout; converting it needs a CUDA device "
+                                           "(eetq_b200 has no CPU path)")
+                    src = w if w.is_cuda else w.cuda()
+                    state_dict = dict(state_dict)  # do not touch the caller's dict
+                    state_dict[wkey] = convert_ref_checkpoint_weight(src.contiguous()).to(w.device)
+                    state_dict[lkey] = torch.tensor([B200_LAYOUT], dtype=torch.int32)
+            else:
+                marker = int(state_dict[lkey].reshape(-1)[0])
+                if marker != B200_LAYOUT:
+                    error_msgs.append(f"{lkey} = {marker}: unknown weight layout (this build understands {B200_LAYOUT})")
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
+def export_reference_state_dict(model: nn.Module) -> dict:
+    """``model.state_dict()`` with every quantised weight converted back to the reference's interleaved bytes and the layout
+    markers dropped: loadable by reference EETQ / Hugging Face ``EetqLinear`` (python/eetq/models/base.py:108-146)."""
+    sd = dict(model.state_dict())
+    for name, mod in model.named_modules():
+        if isinstance(mod, _LayoutAwareMixin):
+            prefix = name + "." if name else ""
+            wkey = prefix + mod._weight_key
+            w = sd[wkey]
+            src = w if w.is_cuda else w.cuda()
+            sd[wkey] = to_ref_checkpoint_weight(src.contiguous()).to(w.device)
+            sd.pop(prefix + _LAYOUT_KEY, None)
+    return sd
 
 _FLOAT_WEIGHT_DTYPES = (torch.float16, torch.bfloat16, torch.float32)
 
@@ -49,13 +108,16 @@ def _activation_dtype_for(weight_dtype: torch.dtype) -> torch.dtype:
     return weight_dtype if weight_dtype in (torch.float16, torch.bfloat16) else torch.float16
 
 
-class W8A16Linear(nn.Module):
+class W8A16Linear(_LayoutAwareMixin, nn.Module):
     """Weight-only int8 linear layer; drop-in for ``nn.Linear`` at inference time."""
+
+    _weight_key = "qweight"
 
     def __init__(self, in_features: int, out_features: int, bias: bool = True, dev="cuda:0", dtype: torch.dtype = torch.float16):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         self.register_buffer("qweight", torch.zeros(in_features, out_features, dtype=torch.int8, device=dev))
+        self._register_layout_marker(dev)
         self.register_buffer("weight_scales", torch.zeros(out_features, dtype=dtype, device=dev))
         if bias:
             self.register_buffer("bias", torch.zeros(out_features, dtype=dtype, device=dev))
@@ -108,14 +170,17 @@ class EetqLinearMMFunction(Function):
         return grad_output.matmul(dequantised.t()), None, None, None
 
 
-class EetqLinear(nn.Module):
+class EetqLinear(_LayoutAwareMixin, nn.Module):
     """The layer Hugging Face transformers instantiates for ``quant_method="eetq"``: int8 ``weight`` now, scales later."""
+
+    _weight_key = "weight"
 
     def __init__(self, in_features: int, out_features: int, bias: bool = True, device="cuda:0", dtype: torch.dtype = torch.float16):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         self._act_dtype = dtype
         self.register_buffer("weight", torch.zeros(in_features, out_features, dtype=torch.int8, device=device))
+        self._register_layout_marker(device)
         if bias:
             self.register_buffer("bias", torch.zeros(out_features, dtype=dtype, device=device))
         else:

@@ -26,8 +26,8 @@ import torch
 
 from . import _cabi
 
-__all__ = ["quant_weights", "preprocess_weights", "w8_a16_gemm", "w8_a16_gemm_", "w8_a16_gemm_bias",
-           "convert_ref_checkpoint_weight", "to_ref_checkpoint_weight", "unpack_weights"]
+__all__ = ["quant_weights", "preprocess_weights", "w8_a16_gemm", "w8_a16_gemm_", "w8_a16_gemm_bias", "w8_a16_gemm_residual",
+           "convert_ref_checkpoint_weight", "to_ref_checkpoint_weight", "unpack_weights", "rotary_embedding_neox", "layernorm_forward"]
 
 _DTYPE_CODE = {torch.float16: _cabi.F16, torch.bfloat16: _cabi.BF16, torch.float32: _cabi.F32}
 
@@ -181,13 +181,19 @@ def _check_gemm_args(x: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor,
 
 
 def _gemm_into(x2: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor], out2: torch.Tensor,
-               M: int, N: int, K: int, flags: int = _cabi.FLAG_DEFAULT) -> None:
+               M: int, N: int, K: int, flags: int = _cabi.FLAG_DEFAULT, residual: Optional[torch.Tensor] = None) -> None:
     L = _cabi.lib()
     ws_bytes = int(L.eetq_b200_workspace_bytes(M, N, K)) if M > 4 else 0
     ws = _workspace(x2.device, ws_bytes)
     # a single row has no meaningful row stride (torch allows anything there): pass the contiguous value
     ldx = x2.stride(0) if M > 1 else K
     ldy = out2.stride(0) if M > 1 else N
+    if residual is not None:
+        rc = L.eetq_b200_w8a16_gemm_residual(_vp(x2), ldx, _vp(weight), _vp(scale), _vp(bias), _vp(residual),
+                                             residual.stride(0) if M > 1 else N, _vp(out2), ldy, M, N, K, _DTYPE_CODE[x2.dtype], _vp(ws),
+                                             0 if ws is None else ws.numel(), flags, _stream())
+        _cabi.check(rc, "eetq_b200_w8a16_gemm_residual")
+        return
     rc = L.eetq_b200_w8a16_gemm_ex(_vp(x2), ldx, _vp(weight), _vp(scale), _vp(bias), _vp(out2), ldy, M, N, K,
                                    _DTYPE_CODE[x2.dtype], _vp(ws), 0 if ws is None else ws.numel(), flags, _stream())
     _cabi.check(rc, "eetq_b200_w8a16_gemm")
@@ -210,6 +216,28 @@ def w8_a16_gemm_bias(input: torch.Tensor, weight: torch.Tensor, scale: torch.Ten
     return out
 
 
+def w8_a16_gemm_residual(input: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, residual: torch.Tensor,
+                         bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``residual + w8_a16_gemm(input, ...)`` with the add fused into the kernel epilogue (fp16 add of the rounded product,
+    like ``hidden = residual + o_proj(x)``).  ``residual`` is ``[M, N]`` with unit inner stride (any 8-aligned row stride)."""
+    _check_gemm_args(input, weight, scale, bias)
+    K, N = weight.shape
+    x2 = input.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0) or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    r2 = residual.reshape(-1, N)
+    if r2.shape[0] != M or r2.dtype != input.dtype or r2.device != input.device:
+        raise RuntimeError("w8_a16_gemm_residual: residual must be [M, N] of input's dtype on input's device")
+    if r2.stride(-1) != 1 or (M > 1 and r2.stride(0) % 8 != 0) or r2.data_ptr() % 16 != 0:
+        r2 = r2.contiguous()
+    out = torch.empty(input.shape[:-1] + (N,), dtype=input.dtype, device=input.device)
+    if M > 0:
+        with torch.cuda.device(input.device):
+            _gemm_into(x2, weight, scale, bias, out.view(-1, N), M, N, K, residual=r2)
+    return out
+
+
 def w8_a16_gemm(input: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """y = input @ dequant(weight) ; callee allocates the output on input's device with input's dtype
     (fpA_intB_gemm_wrapper.cu:139-140).  Any leading shape is accepted (the reference handles 2-D and 3-D)."""
@@ -228,3 +256,44 @@ def w8_a16_gemm_(input: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor,
         with torch.cuda.device(input.device):
             _gemm_into(input.view(m, k), weight, scale, None, output.view(m, n), m, n, k)
     return output
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the two glue ops the reference module also exports (csrc/eetpy.cpp:18-19)
+# ---------------------------------------------------------------------------------------------------------------
+def rotary_embedding_neox(positions: torch.Tensor, query: torch.Tensor, key: torch.Tensor, head_size: int,
+                          cos_sin_cache: torch.Tensor) -> None:
+    """In-place GPT-NeoX rotary embedding of ``query`` and ``key`` (``[..., num_heads, head_size]`` fp16, contiguous),
+    ``positions`` int64 ``[num_tokens]``, ``cos_sin_cache`` ``[max_position, rot_dim]`` = cos | sin halves -- same
+    arguments, in-place semantics and fp16 arithmetic as the reference (pos_encoding_kernels.cu:12-87)."""
+    if query.dtype != torch.float16 or key.dtype != torch.float16 or cos_sin_cache.dtype != torch.float16:
+        raise RuntimeError("rotary_embedding_neox: fp16 tensors expected")
+    if not (query.is_cuda and key.is_cuda and positions.is_cuda and cos_sin_cache.is_cuda):
+        raise RuntimeError("rotary_embedding_neox: CUDA tensors expected (eetq_b200 has no CPU path)")
+    if not (query.is_contiguous() and key.is_contiguous() and cos_sin_cache.is_contiguous()) or positions.dtype != torch.int64:
+        raise RuntimeError("rotary_embedding_neox: contiguous tensors and int64 positions expected")
+    num_heads = query.shape[-2]
+    num_tokens = query.numel() // (num_heads * head_size)
+    if key.shape != query.shape or query.shape[-1] != head_size or positions.numel() != num_tokens:
+        raise RuntimeError("rotary_embedding_neox: shape mismatch")
+    with torch.cuda.device(query.device):
+        rc = _cabi.lib().eetq_b200_rotary_embedding_neox(_vp(positions.contiguous()), _vp(query), _vp(key), num_tokens, num_heads, head_size,
+                                                          _vp(cos_sin_cache), cos_sin_cache.shape[1], _stream())
+        _cabi.check(rc, "eetq_b200_rotary_embedding_neox")
+
+
+def layernorm_forward(input: torch.Tensor, gamma: torch.Tensor, out: torch.Tensor, eps: float) -> None:
+    """T5-style RMS norm of the rows of ``input`` ``[b, n, c]`` fp16 into ``out`` (layernorm.cu:88-110)."""
+    if input.dtype != torch.float16 or gamma.dtype != torch.float16 or out.dtype != torch.float16:
+        raise RuntimeError("layernorm_forward: fp16 tensors expected")
+    if not (input.is_cuda and gamma.is_cuda and out.is_cuda):
+        raise RuntimeError("layernorm_forward: CUDA tensors expected (eetq_b200 has no CPU path)")
+    if not (input.is_contiguous() and out.is_contiguous() and gamma.is_contiguous()) or out.shape != input.shape:
+        raise RuntimeError("layernorm_forward: contiguous tensors of equal shape expected")
+    n = input.shape[-1]
+    m = input.numel() // n
+    if gamma.numel() != n:
+        raise RuntimeError("layernorm_forward: gamma must have input.shape[-1] elements")
+    with torch.cuda.device(input.device):
+        rc = _cabi.lib().eetq_b200_layernorm_forward(_vp(input), _vp(gamma), _vp(out), m, n, float(eps), _stream())
+        _cabi.check(rc, "eetq_b200_layernorm_forward")

@@ -10,9 +10,20 @@ import torch
 from torch import nn
 
 from ..modules.qlinear import W8A16Linear
-from .base import find_layers, set_op_by_name
+from .base import find_layers, find_submodule, get_named_linears, set_op_by_name
 
-__all__ = ["eet_quantize"]
+__all__ = ["eet_quantize", "replace_with_eet_qlinear", "structure_mapping"]
+
+# name of the decoder-layer container per model family (python/eetq/utils/mapping.py:1-18)
+_DECODER_CONTAINER = {"llama": "layers", "baichuan": "layers"}
+
+
+def structure_mapping(model: nn.Module, target_model: str = "llama") -> dict:
+    """``{"decoder": <attribute name of the ModuleList of decoder layers>}`` for a supported family."""
+    try:
+        return {"decoder": _DECODER_CONTAINER[target_model]}
+    except KeyError:
+        raise NotImplementedError(f"structure_mapping: unsupported model family {target_model!r}") from None
 
 
 def _to_w8a16(linear: nn.Module, init_only: bool) -> W8A16Linear:
@@ -37,3 +48,13 @@ def eet_quantize(model: nn.Module, init_only: bool = False, include=(nn.Linear,)
         if verbose:
             print("[EET][INFO] quantized {}".format(dotted_name))
     return model
+
+
+def replace_with_eet_qlinear(model: nn.Module, init_only: bool = False, target_model: str = "llama", device="cuda:0") -> None:
+    """Per-decoder-layer variant of :func:`eet_quantize` (python/eetq/utils/quantizer.py:13-38): every ``nn.Linear`` inside the
+    decoder layers of ``model`` (found through :func:`structure_mapping`) becomes a :class:`W8A16Linear`; modules outside
+    the decoder stack (embeddings, ``lm_head``) are left alone."""
+    layers = find_submodule(model, structure_mapping(model, target_model)["decoder"])
+    for layer in layers:
+        for dotted_name, linear in get_named_linears(layer).items():
+            set_op_by_name(layer, dotted_name, _to_w8a16(linear, init_only))

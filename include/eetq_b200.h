@@ -146,78 +146,95 @@ int eetq_b200_w8a16_gemm_host(const void* x_host, void* x_dev, const int8_t* w_b
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Decode-side extensions (SURVEY.md section 8 "next", rank 2 and 4) -- NOT part of the reference's w8a16 boundary.
- * They exist so the headline metric (Llama-2-7B decode tokens/s) is bounded by the weight stream, not by
- * framework-op launches.  fp16 only, single token.  `pdl` != 0 launches with programmatic dependent launch.
+ * Extensions either side of the w8a16 linears (SURVEY.md section 8 "next", ranks 2 and 4) -- NOT part of the reference's
+ * w8a16 boundary, except eetq_b200_rotary_embedding_neox / eetq_b200_layernorm_forward which stand in for the two glue
+ * ops the reference module also exports (csrc/eetpy.cpp:18-19).  They exist so that the headline metric (Llama-2-7B decode
+ * tokens/s) is bounded by the weight stream, not by framework-op launches.  fp16.  `pdl` != 0 launches with programmatic
+ * dependent launch.
  *
- * eetq_b200_w8a16_gemv_fused: the decode GEMV (M <= 8) with glue folded in:
- *   xmode 0: plain;  1: x := RMSNorm(x; norm_weight, eps) on load (HF LlamaRMSNorm arithmetic; replaces the
- *   reference's separate generalT5LayerNorm kernel, csrc/layernorm_kernels/layernorm.cu:25-51);
- *   2: x := silu(x[:, :K]) * x[:, K:2K] (fused gate|up activation; ldx >= 2K);
- *   residual != NULL: y = dtype(acc * s [+ bias]) + residual  (the reference never wired FT's residual epilogues,
- *   fpA_intB_gemm_template.h:492-537).
+ * Multi-GPU exchange ("LL" buffers): a vector of E fp16 values that every rank needs is kept, on every rank, as E/2 8-byte
+ * words {two values, 32-bit tag}.  A producer stores its words with single 8-byte stores straight into every rank's copy
+ * (peer-mapped symmetric memory over NVLink); a consumer polls the words it is about to use until their tag matches
+ * tag = *step * per_step + index + 1.  `step` is a device int32 that eetq_b200_lm_head_argmax increments once per decode
+ * step; `index` numbers the exchanges inside one step (0 <= index < per_step).  This is the fused replacement of "one
+ * all-gather of the activations per sharded linear" (SURVEY.md section 8e): no collective call, no fence, no flag.
  * ------------------------------------------------------------------------------------------- */
-int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias,
-                               const void* norm_weight, float eps, int xmode, const void* residual, int64_t ldr, void* y,
-                               int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, int pdl, void* stream);
-/* eetq_b200_w8a16_gemv_fused that also issues an L2 prefetch of the KV-cache rows [0, *pos) ([heads][max_ctx][128] fp16)
- * the attention kernel launched right after it will read (the GEMV's own weight stream is already in flight). */
-int eetq_b200_w8a16_gemv_fused_kvprefetch(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
-                                          float eps, int xmode, const void* residual, int64_t ldr, void* y, int64_t ldy, int64_t M,
-                                          int64_t N, int64_t K, int dtype, const void* kcache, const void* vcache, const void* pos_i32,
-                                          int64_t heads, int64_t max_ctx, int pdl, void* stream);
+typedef struct eetq_b200_ll {        /* consumer side: which exchange a buffer currently carries */
+    const void* step;                /* device int32 step counter; NULL = the buffer is a plain fp16 vector */
+    int per_step;
+    int index;
+} eetq_b200_ll;
 
-/* Up to 4 DEPENDENT decode GEMVs (M = 1, fp16; e.g. o_proj -> gate|up -> down -> next layer's q|k|v) in ONE launch:
- * the CTAs meet at a grid barrier between phases but issue the next phase's first weight loads before waiting, so the
- * HBM stream does not stop at what would otherwise be kernel boundaries.  counters: nphases-1 uint32 private to this call
- * site, zero on first use (they only increase); epoch: device int32 >= 1 that increases by exactly 1 per launch. */
-typedef struct eetq_b200_gemv_phase {
-    const void* x;            /* activation [K] (or [2K] for xmode 2) */
-    int64_t ldx;
-    const void* w;            /* b200 layout, N*K bytes */
-    const void* scales;       /* [N] fp16 */
-    void* y;                  /* [N] fp16 */
-    int64_t N, K;
-    const void* norm_weight;  /* xmode 1 */
-    const void* residual;     /* [N] or NULL */
+typedef struct eetq_b200_ll_push {   /* producer side */
+    int world;                       /* number of ranks (1..8) */
+    const uint64_t* peers;           /* [world] HOST array: device address of the LL buffer on every rank, index = rank */
+    void* local;                     /* this rank's own copy */
+    int64_t elem_off;                /* first element of this rank's slice inside the full vector (even) */
+    const void* step;                /* device int32 step counter */
+    int per_step;
+    int index;
+} eetq_b200_ll_push;
+
+/* eetq_b200_w8a16_gemv_fused: the decode GEMV (M <= 8) with glue folded in (all fields optional / zero):
+ *   xmode 0: plain;  1: x := RMSNorm(x; norm_weight, eps) on load (HF LlamaRMSNorm arithmetic; replaces the reference's
+ *   separate generalT5LayerNorm launch);  2: x := silu(x[:, :K]) * x[:, K:2K] (ldx >= 2K);
+ *   epi 0: plain;  1: weight rows are interleaved (gate_0, up_0, gate_1, up_1, ...) and the kernel emits the N/2 values
+ *   fp16(silu(fp16 gate)) * fp16 up  (`act_fn(gate_proj(x)) * up_proj(x)`), no bias;
+ *   residual != NULL: y = dtype(acc * s [+ bias]) + residual  (the reference never wired FT's residual epilogues,
+ *   fpA_intB_gemm_template.h:492-537);
+ *   x_ll / residual_ll / push (M = 1, fp16): x / residual are LL buffers of the FULL vectors (residual_off = element
+ *   offset of this rank's output slice), outputs are pushed to every rank's LL buffer instead of being stored to y. */
+typedef struct eetq_b200_gemv_opts {
+    const void* norm_weight;
     float eps;
-    int xmode;                /* 0 plain, 1 RMSNorm on load, 2 silu(x[:K]) * x[K:2K] */
-} eetq_b200_gemv_phase;
-int eetq_b200_w8a16_gemv_chain(const void* phases, int nphases, void* counters, const void* epoch, int pdl, void* stream);
+    int xmode;
+    int epi;
+    const void* residual;
+    int64_t ldr;
+    const eetq_b200_ll* x_ll;
+    const eetq_b200_ll* residual_ll;
+    int64_t residual_off;
+    const eetq_b200_ll_push* push;
+} eetq_b200_gemv_opts;
+int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias, void* y,
+                               int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, const eetq_b200_gemv_opts* opts, int pdl,
+                               void* stream);
 
-/* Column-sharded decode GEMV with the activation all-gather FUSED into the epilogue over NVLink peer memory
- * (one all-gather per sharded linear).  Rank r owns rows [r*N/P, (r+1)*N/P) of the linear; every
- * rank stores its slice straight into all ranks' copies of the output vector (peer-mapped symmetric memory) and the last
- * CTA publishes flags[slot][rank] = *epoch on every peer (st.release.sys).  The kernel that CONSUMES the vector waits for
- * all ranks' flags of that slot (`wait_flags`, ld.acquire.sys) in its prologue.  peer_y[r]: rank r's output buffer offset to this rank's
- * first row; peer_flag[r]: address on rank r of flags[slot][this rank]; local_flags: this rank's flags[slot][0..world);
- * ticket: local uint32 (zero between calls); epoch: device int32, strictly increasing per decode step. */
-int eetq_b200_w8a16_gemv_fused_p2p(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* norm_weight,
-                                   float eps, int xmode, const void* residual, int64_t ldr, int64_t M, int64_t N_local, int64_t K,
-                                   int dtype, int world, const uint64_t* peer_y, const uint64_t* peer_flag, const void* local_flags,
-                                   const void* wait_flags, void* ticket, const void* epoch, int64_t ldy, int pdl, void* stream);
-/* Consumers of a gathered buffer poll the flags of the call that produced it (wait_flags = that call's local_flags, or
- * NULL when the input is local) in their prologue -- after their own weight / KV prefetch -- instead of the producer
- * waiting at its tail.  Same kernels as eetq_b200_decode_rmsnorm / _attention with that wait added. */
-int eetq_b200_decode_rmsnorm_p2p(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, const void* wait_flags,
-                                 int world, const void* epoch, int pdl, void* stream);
-int eetq_b200_decode_attention_p2p(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
-                                   void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
-                                   const void* wait_flags, int world, const void* epoch, int pdl, void* stream);
-/* x[0:H] = table[*token] */
-int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, int pdl, void* stream);
-/* y = RMSNorm(x) * w over M rows of H */
-int eetq_b200_decode_rmsnorm(const void* x, const void* w, void* y, int64_t M, int64_t H, float eps, int pdl, void* stream);
-/* Fused RoPE (rotate_half convention; behaviour of rotary_embedding_neox, csrc/embedding_kernels/pos_encoding_kernels.cu:12-53)
- * + KV-cache append + split-KV attention + split merge for ONE token at position *pos, head_dim 128, ONE launch.
- *   qkv [3H] = q | k | v raw projections; cos/sin [max_pos][D/2]; kcache/vcache [H/D][max_ctx][D], head-major so each
- *   CTA streams one contiguous block (row *pos of every head is written);
- *   partial: (H/D) * eetq_b200_decode_attention_splits(max_ctx) * 130 floats of scratch; tickets: H/D int32, zero on first
- *   use (left zero); out [H]. */
-int64_t eetq_b200_decode_attention_splits(int64_t max_ctx);
+/* x[0:H] = table[*token] (plain vector, or LL words with the tag of x_ll when x_ll != NULL) */
+int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, const eetq_b200_ll* x_ll, int pdl, void* stream);
+/* y[m] = RMSNorm(x[m]) * w over M rows of H (HF LlamaRMSNorm arithmetic), row strides ldx / ldy elements */
+int eetq_b200_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int64_t M, int64_t H, float eps, int pdl, void* stream);
+/* layernorm_forward of the reference (csrc/eetpy.cpp:19 -> layernorm_kernels/layernorm.cu:88-110): fp16 [m, n] rows,
+ * T5-style RMS norm, out = fp16(clamp((x * rsqrt(mean(x^2) + eps)) * gamma)) with ONE rounding. */
+int eetq_b200_layernorm_forward(const void* input, const void* gamma, void* out, int64_t m, int64_t n, float eps, void* stream);
+/* rotary_embedding_neox of the reference (csrc/eetpy.cpp:18 -> embedding_kernels/pos_encoding_kernels.cu:55-87): in place on
+ * query and key [num_tokens, num_heads, head_size] fp16; cos_sin_cache [max_position, rot_dim] = cos | sin halves. */
+int eetq_b200_rotary_embedding_neox(const void* positions_i64, void* query, void* key, int64_t num_tokens, int64_t num_heads,
+                                    int64_t head_size, const void* cos_sin_cache, int64_t rot_dim, void* stream);
+/* Prefill glue: rotate q (in place) and k of T tokens at cache positions p0 .. p0+T-1 (HF rotate_half convention, cos/sin
+ * tables [max_pos][D/2]) and write rotated k and v into the head-major KV cache [heads][max_ctx][D]; qkv rows = q | k | v. */
+int eetq_b200_prefill_rope_kv(void* qkv, int64_t ld, const void* cos_t, const void* sin_t, void* kcache, void* vcache, int64_t T,
+                              int64_t heads, int64_t D, int64_t max_ctx, int64_t p0, void* stream);
+/* Prefill glue: act[t][i] = fp16(silu(gate)) * up; interleaved = 0: rows are gate[I] | up[I], 1: (g0, u0, g1, u1, ...) */
+int eetq_b200_silu_mul(const void* gu, int64_t ldg, void* act, int64_t lda, int64_t T, int64_t I, int interleaved, void* stream);
+/* Fused RoPE (rotate_half convention) + KV-cache append + attention for ONE token at position *pos, head_dim 128, ONE
+ * launch: grid (local heads, 8) in clusters of 8 CTAs per head; the KV stream is register-fed and starts before the
+ * dependency wait; the 8 partial results of a head are merged through distributed shared memory.
+ *   qkv [3 * H_local] = q | k | v raw projections of this rank's heads; cos/sin [max_pos][D/2]; kcache/vcache
+ *   [H_local/D][max_ctx][D] head-major (row *pos of every head is written); out [H_local] plain fp16, or NULL and `push`
+ *   describes the LL exchange of the full attention vector (elem_off = first element of this rank's heads). */
 int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
-                               void* vcache, void* partial, void* tickets, void* out, int64_t H, int64_t D, int64_t max_ctx,
+                               void* vcache, void* out, int64_t H_local, int64_t D, int64_t max_ctx, const eetq_b200_ll_push* push,
                                int pdl, void* stream);
+/* Final RMSNorm + fp16 lm_head (the reference leaves lm_head unquantised, quantizer.py:40) + greedy arg-max in ONE launch:
+ *   logits[v] = RMSNorm(x; norm_w, eps) . W[v, :] over this rank's V_local vocabulary rows (global ids v_begin ..); the last CTA
+ *   picks the winner (first maximum), exchanges candidates with the other ranks when `cand` is given, writes *token (int64),
+ *   and advances *pos and *step by one.  logits (optional) receives the fp16 logits of this rank's rows at their global ids.
+ *   scratch: eetq_b200_lm_head_scratch_bytes() bytes, zero on first use (left clean). */
+size_t eetq_b200_lm_head_scratch_bytes(void);
+int eetq_b200_lm_head_argmax(const void* x, const eetq_b200_ll* x_ll, const void* norm_w, float eps, const void* w, int64_t V_local,
+                             int64_t H, int64_t v_begin, void* logits, void* scratch, void* token_i64, void* pos_i32, void* step_i32,
+                             const eetq_b200_ll_push* cand, int rank, int pdl, void* stream);
 
 /* number of kernels this library has launched on this process so far (bench.py's gpu_launches) */
 uint64_t eetq_b200_launch_count(void);

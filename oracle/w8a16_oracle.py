@@ -139,6 +139,39 @@ def cpu_dequant_matmul(x: torch.Tensor, q_kn: torch.Tensor, scales: torch.Tensor
     return (x.float() @ wd.float()).to(x.dtype)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# glue ops the reference module also exports (csrc/eetpy.cpp:18-19).  CUDA-only in the reference (they cannot be built
+# without a GPU), so these restatements follow the kernels' arithmetic line by line: parity for them is "unpinned" in the
+# sense of the task text (no golden vectors, no executable reference) and rests on this restatement alone.
+# ---------------------------------------------------------------------------------------------------------------
+def rotary_embedding_neox(positions: torch.Tensor, query: torch.Tensor, key: torch.Tensor, head_size: int,
+                          cos_sin_cache: torch.Tensor):
+    """csrc/embedding_kernels/pos_encoding_kernels.cu:12-53.  query/key [num_tokens, num_heads, head_size] fp16;
+    cos_sin_cache [max_position, rot_dim] = cos | sin; returns rotated COPIES.  Every product and the final
+    difference / sum are separate fp16 operations (``q_x * cos - q_y * sin`` on ``__half`` operands)."""
+    rot = cos_sin_cache.shape[1]
+    e = rot // 2
+    q, k = query.clone(), key.clone()
+    cs = cos_sin_cache[positions.long()]                       # [T, rot]
+    c, s = cs[:, None, :e], cs[:, None, e:]                    # broadcast over heads
+
+    def rot_half(t):
+        x, y = t[..., :e].clone(), t[..., e:rot].clone()
+        t[..., :e] = (x * c).half() - (y * s).half()           # each torch op on fp16 tensors rounds once
+        t[..., e:rot] = (y * c).half() + (x * s).half()
+        return t
+
+    return rot_half(q), rot_half(k)
+
+
+def layernorm_forward(x: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
+    """csrc/layernorm_kernels/layernorm.cu:25-51 (generalT5LayerNorm): fp32 variance of each row, ONE fp16 rounding of
+    ``(x * rsqrt(var + eps)) * gamma`` clamped to the fp16 range (clamp_inf_for_half)."""
+    xf = x.float()
+    r = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return ((xf * r) * gamma.float()).clamp(-65504.0, 65504.0).half()
+
+
 def norm_rel_err(y: torch.Tensor, y_ref: torch.Tensor) -> float:
     """The parity metric of BASELINE.md §5: ``max|y - y_ref| / max|y_ref|``."""
     d = (y.double() - y_ref.double()).abs().max().item()

@@ -57,11 +57,33 @@ def test_same_seed_gives_identical_models_on_every_rank():
         assert na == nb and torch.equal(pa, pb)
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_llama_shapes_shard_in_multiples_of_64(world):
-    """Column shards of every fused Llama-2-7B / 13B linear must stay multiples of 64 rows (kernel constraint)."""
-    from eetq_b200.decode import LLAMA2_7B, LLAMA2_13B
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_shard_plan_llama_shapes(world):
+    """Every rank's block of every (fused) Llama-2-7B / 13B linear stays a multiple of 64 rows (kernel constraint), the
+    blocks tile the full matrices, and the exchange indices of a decode step are all distinct."""
+    from eetq_b200.decode import LLAMA2_7B, LLAMA2_13B, shard_plan
 
     for s in (LLAMA2_7B, LLAMA2_13B):
-        for n in (3 * s.hidden, s.hidden, 2 * s.inter, s.hidden):
-            assert n % (64 * world) == 0, (s.name, n, world)
+        heads, hidden, inter, vocab = [], [], [], []
+        for r in range(world):
+            p = shard_plan(s, r, world)
+            heads.append(p["heads"]); hidden.append(p["hidden"]); inter.append(p["inter"]); vocab.append(p["vocab"])
+            hl = p["heads"][1] - p["heads"][0]
+            for n in (3 * hl * s.head_dim, p["hidden"][1] - p["hidden"][0], 2 * (p["inter"][1] - p["inter"][0])):
+                assert n % 64 == 0, (s.name, world, n)
+        for spans, total in ((heads, s.heads), (hidden, s.hidden), (inter, s.inter), (vocab, s.vocab)):
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        p = shard_plan(s, 0, world)
+        idx = [0] + [f(l) for l in range(s.layers) for f in (p["attn"], p["x2"], p["act"], p["x_out"])] + [p["cand"]]
+        assert len(set(idx)) == len(idx) and max(idx) < p["per_step"]
+        assert all(p["x_in"](l + 1) == p["x_out"](l) for l in range(s.layers - 1)) and p["x_in"](0) == 0
+
+
+def test_shard_plan_rejects_impossible_splits():
+    from eetq_b200.decode import shard_plan
+
+    with pytest.raises(ValueError):
+        shard_plan(LlamaShape(hidden=4096, inter=11008, layers=2, heads=32), 0, 3)
+    with pytest.raises(ValueError):
+        shard_plan(TINY, 0, 4)      # 2 heads cannot be split 4-way

@@ -55,18 +55,63 @@ def test_set_op_by_name_handles_indices():
 def test_w8a16linear_buffers_and_state_dict_keys():
     q = W8A16Linear(128, 64, bias=True, dev="cpu")
     sd = q.state_dict()
-    assert sorted(sd) == ["bias", "qweight", "weight_scales"]            # qlinear.py:34-38
+    # qlinear.py:34-38 + the layout marker that tells b200 bytes from reference-layout bytes
+    assert sorted(sd) == ["bias", "qweight", "weight_layout", "weight_scales"]
+    assert int(sd["weight_layout"][0]) == eetq_b200.B200_LAYOUT
     assert sd["qweight"].shape == (128, 64) and sd["qweight"].dtype == torch.int8
     assert sd["weight_scales"].shape == (64,) and sd["weight_scales"].dtype == torch.float16
     q2 = W8A16Linear(128, 64, bias=False, dev="cpu")
-    assert q2.bias is None and sorted(q2.state_dict()) == ["qweight", "weight_scales"]
+    assert q2.bias is None and sorted(q2.state_dict()) == ["qweight", "weight_layout", "weight_scales"]
 
 
 def test_eetqlinear_late_scale_registration():
     q = EetqLinear(128, 64, bias=False, device="cpu")
-    assert sorted(q.state_dict()) == ["weight"]                          # qlinear.py:103
+    assert sorted(q.state_dict()) == ["weight", "weight_layout"]         # qlinear.py:103 (+ marker)
     q.register_scale("cpu")
-    assert sorted(q.state_dict()) == ["weight", "weight_scales"]         # qlinear.py:113-116
+    assert sorted(q.state_dict()) == ["weight", "weight_layout", "weight_scales"]   # qlinear.py:113-116
+
+
+@pytest.mark.parametrize("cls,key", [(W8A16Linear, "qweight"), (EetqLinear, "weight")])
+def test_state_dict_layout_marker_decides_conversion(monkeypatch, cls, key):
+    """A state dict WITHOUT the marker comes from a reference build (sm80 interleaved bytes): the weight goes through the
+    layout converter on load.  One WITH the marker is loaded verbatim; an unknown marker value is an error.  The converter
+    (a GPU kernel) is stubbed here: this checks the host logic."""
+    import eetq_b200.modules.qlinear as ql
+
+    calls = []
+
+    def fake_convert(w):
+        calls.append(w.clone())
+        return (w.to(torch.int16) + 1).to(torch.int8)
+
+    monkeypatch.setattr(ql, "convert_ref_checkpoint_weight", fake_convert)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    kw = dict(dev="cpu") if cls is W8A16Linear else dict(device="cpu")
+    src = cls(64, 64, bias=False, **kw)
+    if cls is EetqLinear:
+        src.register_scale("cpu")
+    getattr(src, key).copy_(torch.randint(-100, 100, (64, 64), dtype=torch.int8))
+    sd = src.state_dict()
+
+    same = cls(64, 64, bias=False, **kw)
+    if cls is EetqLinear:
+        same.register_scale("cpu")
+    same.load_state_dict(sd)                                   # b200 checkpoint: verbatim
+    assert not calls and torch.equal(getattr(same, key), getattr(src, key))
+
+    ref_sd = {k: v for k, v in sd.items() if k != "weight_layout"}      # what a reference build would have written
+    conv = cls(64, 64, bias=False, **kw)
+    if cls is EetqLinear:
+        conv.register_scale("cpu")
+    conv.load_state_dict(ref_sd)                               # strict load succeeds: the marker is synthesised
+    assert len(calls) == 1 and torch.equal(getattr(conv, key), getattr(src, key) + 1)
+    assert "weight_layout" not in ref_sd                       # the caller's dict is left untouched
+
+    bad = dict(sd)
+    bad["weight_layout"] = torch.tensor([7], dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="unknown weight layout"):
+        cls(64, 64, bias=False, **kw).load_state_dict(bad, strict=False)
 
 
 def test_eet_quantize_init_only_builds_skeleton():
