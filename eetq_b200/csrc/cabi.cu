@@ -81,14 +81,17 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 // shared argument validation of every w8a16 forward entry point
 int check_forward_args(const char* who, const void* x, int64_t ldx, const void* w, const void* scales, const void* y, int64_t ldy,
-                       int64_t M, int64_t N, int64_t K, int dtype)
+                       int64_t M, int64_t N, int64_t K, int dtype, int64_t n_out)
 {
+    if (n_out < 0)
+        n_out = N;  // output row width (N / 2 for the SiLU*up pair epilogue)
     EB_CHECK_ARG(x && w && scales && y, "%s: null pointer argument", who);
     EB_CHECK_ARG(dtype == EETQ_B200_F16 || dtype == EETQ_B200_BF16, "%s: dtype must be F16 or BF16 (got %d)", who, dtype);
     EB_CHECK_ARG(M >= 0 && M <= (int64_t(1) << 24), "%s: bad M=%lld", who, (long long)M);
     if (int rc = check_kn(who, K, N))
         return rc;
-    EB_CHECK_ARG(ldx >= K && ldy >= N, "%s: ldx (%lld) < K or ldy (%lld) < N", who, (long long)ldx, (long long)ldy);
+    EB_CHECK_ARG(ldx >= K && ldy >= n_out, "%s: ldx (%lld) < K or ldy (%lld) < output width (%lld)", who, (long long)ldx, (long long)ldy,
+                 (long long)n_out);
     EB_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0, "%s: ldx and ldy must be multiples of 8 elements", who);
     EB_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y), "%s: x, w and y must be 16-byte aligned", who);
     return EETQ_B200_OK;
@@ -248,7 +251,8 @@ int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200,
     // LL buffers are 8-byte words, not element vectors: validate what applies
     void* y_chk     = push ? const_cast<int8_t*>(w_b200) : y;
     const int64_t kx = (o->xmode == GEMV_X_SILU_MUL) ? 2 * K : K;
-    if (int rc = check_forward_args("w8a16_gemv_fused", x, x_ll ? K : ldx, w_b200, scales, y_chk, push ? N : ldy, M, N, K, dtype))
+    const int64_t n_out = (o->epi == GEMV_EPI_SILU_PAIRS) ? N / 2 : N;
+    if (int rc = check_forward_args("w8a16_gemv_fused", x, x_ll ? K : ldx, w_b200, scales, y_chk, push ? N : ldy, M, N, K, dtype, n_out))
         return rc;
     EB_CHECK_ARG(M >= 1 && M <= EETQ_B200_GEMV_MAX_M, "w8a16_gemv_fused: M must be in [1, %d]", EETQ_B200_GEMV_MAX_M);
     EB_CHECK_ARG(o->xmode >= 0 && o->xmode <= 2 && (o->xmode != GEMV_X_RMSNORM || (o->norm_weight != nullptr && aligned16(o->norm_weight))),

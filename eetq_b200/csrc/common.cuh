@@ -131,7 +131,7 @@ int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales,
 // argument checks shared by every forward entry point (cabi.cu)
 int check_arch();
 int check_forward_args(const char* who, const void* x, int64_t ldx, const void* w, const void* scales, const void* y, int64_t ldy,
-                       int64_t M, int64_t N, int64_t K, int dtype);
+                       int64_t M, int64_t N, int64_t K, int dtype, int64_t n_out = -1);
 
 // tensor-core (mma.sync) streaming kernel for 2 <= M <= 8 decode rows (gemv_mma.cu)
 bool gemv_mma_supported(int M, int64_t K);

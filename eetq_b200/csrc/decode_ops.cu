@@ -48,8 +48,11 @@ cudaError_t launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 
 __global__ void __launch_bounds__(256) embed_kernel(const __half* __restrict__ table, const int64_t* __restrict__ token,
                                                      __half* __restrict__ x, int H, LLTag ll)
 {
-    pdl_launch_dependents();
+    // The embedding is the FIRST kernel of a decode step.  It releases its dependents only after the previous step's last
+    // kernel (lm_head + arg-max, which advances *pos and the step counter) has completed, so every later kernel of this step
+    // may read the position before its own dependency wait.
     pdl_wait_prior_grids();
+    pdl_launch_dependents();
     const int64_t t = *token;
     if (ll.tag_base == nullptr) {
         const uint4* src = reinterpret_cast<const uint4*>(table + t * H);
@@ -104,6 +107,13 @@ __global__ void __launch_bounds__(512) rmsnorm_kernel(const __half* __restrict__
     }
 }
 
+// Individually rounded fp16 operations.  The reference's scalar_t is c10::Half, whose operators go through fp32 and round
+// after EVERY operation (its SASS, rebuilt here for sm_100a: FMUL, F2FP.F16, FADD, F2FP.F16 -- profiles/r02_ref_rotary_sass.txt);
+// __hmul / __hsub on __half would be contracted into one HFMA by ptxas and differ in the last bit.
+__device__ __forceinline__ __half rn_mul(__half a, __half b) { return __float2half_rn(__half2float(a) * __half2float(b)); }
+__device__ __forceinline__ __half rn_add(__half a, __half b) { return __float2half_rn(__half2float(a) + __half2float(b)); }
+__device__ __forceinline__ __half rn_sub(__half a, __half b) { return __float2half_rn(__half2float(a) - __half2float(b)); }
+
 // In-place GPT-NeoX rotary embedding of query and key, the reference's op of the same name
 // (pos_encoding_kernels.cu:12-53): one CTA per token, cos_sin_cache [max_position][rot_dim] = cos(rot/2) | sin(rot/2),
 // fp16 arithmetic exactly as written there (two rounded products, one rounded difference / sum).
@@ -123,11 +133,11 @@ __global__ void rope_neox_kernel(const int64_t* __restrict__ positions, __half* 
         const int64_t iy = ix + embed_dim;
         const __half c = cache[r], s = cache[embed_dim + r];
         const __half qx = query[ix], qy = query[iy];
-        query[ix] = __hsub(__hmul(qx, c), __hmul(qy, s));
-        query[iy] = __hadd(__hmul(qy, c), __hmul(qx, s));
+        query[ix] = rn_sub(rn_mul(qx, c), rn_mul(qy, s));
+        query[iy] = rn_add(rn_mul(qy, c), rn_mul(qx, s));
         const __half kx = key[ix], ky = key[iy];
-        key[ix] = __hsub(__hmul(kx, c), __hmul(ky, s));
-        key[iy] = __hadd(__hmul(ky, c), __hmul(kx, s));
+        key[ix] = rn_sub(rn_mul(kx, c), rn_mul(ky, s));
+        key[iy] = rn_add(rn_mul(ky, c), rn_mul(kx, s));
     }
 }
 
@@ -220,6 +230,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank()
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank)
@@ -230,6 +241,14 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t r
     float v;
     asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
     return v;
+}
+
+__device__ __forceinline__ void st_dsmem_f32(float* local_ptr, uint32_t rank, float v)
+{
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr));
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 
 struct AttnOut {
@@ -247,8 +266,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     __shared__ __align__(16) __half vnew[ATT_D];
     __shared__ float grp_o[8][ATT_D];   // per 16-lane group partial numerators
     __shared__ float grp_ml[8][2];      // per group (max, denominator)
-    __shared__ float cta_o[ATT_D];      // this CTA's merged partial: read by the whole cluster through DSMEM
-    __shared__ float cta_ml[2];
+    __shared__ float mrg_o[ATT_SPLITS][16];  // partial numerators of MY 16 output dims, one row pushed by every CTA of the cluster
+    __shared__ float mrg_ml[ATT_SPLITS][2];  // (max, denominator) of every CTA of the cluster
 
     const int t       = threadIdx.x;
     const int sub     = t & 15;   // which 8-dim slice of the head
@@ -257,34 +276,37 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     const int split   = int(cluster_ctarank());  // == blockIdx.y
 
     pdl_launch_dependents();
+    cluster_arrive_relaxed();  // "I am running": matched by the wait just before the first remote shared-memory store
     const __half* kbase = kcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
     const __half* vbase = vcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
-    uint4 kreg[2][8], vreg[2][8];
-    auto load_chunk = [&](int buf, int chunk) {
+    // two register buffers, always indexed statically (a runtime buffer index would push all 512 bytes per thread into local memory)
+    uint4 kreg0[8], vreg0[8], kreg1[8], vreg1[8];
+    auto load_chunk = [&](uint4 (&kr)[8], uint4 (&vr)[8], int chunk) {
         const int p0 = chunk * ATT_ROWS;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int j  = p0 + i * 8 + rowlane;
-            kreg[buf][i] = (j < max_ctx) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+            const int j = p0 + i * 8 + rowlane;
+            kr[i]       = (j < max_ctx) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int j  = p0 + i * 8 + rowlane;
-            vreg[buf][i] = (j < max_ctx) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+            const int j = p0 + i * 8 + rowlane;
+            vr[i]       = (j < max_ctx) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
         }
     };
     // Rows below the current position were written by earlier STEPS and rows above it are masked out later, so these loads
     // need neither `pos` nor anything the preceding kernel produces.
-    load_chunk(0, split);
-    load_chunk(1, split + ATT_SPLITS);
-    pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV; *pos was advanced by the previous
-                             // step's last kernel (transitively complete once the preceding grid is)
+    load_chunk(kreg0, vreg0, split);
+    load_chunk(kreg1, vreg1, split + ATT_SPLITS);
+    // *pos was advanced by the PREVIOUS step's last kernel, which completed before this step's first kernel released its
+    // dependents (embed_kernel): the position and its rotary row can be fetched ahead of the dependency wait as well
     const int pos = *pos_p;
     float rope_c = 0.f, rope_s = 0.f;
     if (t < ATT_D / 2) {
         rope_c = __half2float(cos_t[int64_t(pos) * (ATT_D / 2) + t]);
         rope_s = __half2float(sin_t[int64_t(pos) * (ATT_D / 2) + t]);
     }
+    pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
     const int new_chunk = pos / ATT_ROWS;
     const bool owns_new = (new_chunk % ATT_SPLITS) == split;
 
@@ -317,14 +339,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     // online softmax state of this 16-lane group (identical in all 16 lanes; each lane owns 8 dims of the numerator)
     float m_run = -INFINITY, l_run = 0.f;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    auto process = [&](int buf, int chunk) {
+    auto process = [&](const uint4 (&kr)[8], const uint4 (&vr)[8], int chunk) {
         const int p0 = chunk * ATT_ROWS;
         float sc[8];
         float cmax = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int j = p0 + i * 8 + rowlane;
-            uint4 kv    = kreg[buf][i];
+            uint4 kv    = kr[i];
             if (j == pos)
                 kv = *reinterpret_cast<const uint4*>(&knew[sub * 8]);  // the row appended by this very launch
             float d = dot8(kv, qf);
@@ -348,7 +370,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
             if (sc[i] != -INFINITY) {
                 const float p = __expf(sc[i] - m_new);
                 l_run += p;
-                uint4 vv = vreg[buf][i];
+                uint4 vv = vr[i];
                 if (j == pos)
                     vv = *reinterpret_cast<const uint4*>(&vnew[sub * 8]);
                 axpy8(p, vv, acc);
@@ -357,12 +379,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
         m_run = m_new;
     };
 
-    int buf = 0;
-    for (int chunk = split; chunk * ATT_ROWS <= pos; chunk += ATT_SPLITS, buf ^= 1) {
-        process(buf, chunk);
-        const int nxt = chunk + 2 * ATT_SPLITS;
-        if (nxt * ATT_ROWS <= pos)
-            load_chunk(buf, nxt);
+    for (int chunk = split; chunk * ATT_ROWS <= pos; chunk += 2 * ATT_SPLITS) {
+        process(kreg0, vreg0, chunk);
+        if ((chunk + 2 * ATT_SPLITS) * ATT_ROWS <= pos)
+            load_chunk(kreg0, vreg0, chunk + 2 * ATT_SPLITS);
+        if ((chunk + ATT_SPLITS) * ATT_ROWS > pos)
+            break;
+        process(kreg1, vreg1, chunk + ATT_SPLITS);
+        if ((chunk + 3 * ATT_SPLITS) * ATT_ROWS <= pos)
+            load_chunk(kreg1, vreg1, chunk + 3 * ATT_SPLITS);
     }
 
     // merge the 8 groups of this CTA
@@ -387,34 +412,32 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
             num = fmaf(w, grp_o[r][t], num);
             den = fmaf(w, grp_ml[r][1], den);
         }
-        cta_o[t] = num;
-        if (t == 0) {
-            cta_ml[0] = mm;
-            cta_ml[1] = den;
+        // push: dim t is finished by CTA t / 16 of the cluster; every CTA needs every (max, denominator).  (The wait completes the
+        // start-of-kernel phase: every sibling is executing, its shared memory may be written -- it never blocks in practice.)
+        cluster_wait();
+        st_dsmem_f32(&mrg_o[split][t & 15], uint32_t(t >> 4), num);
+        if (t < ATT_SPLITS) {
+            st_dsmem_f32(&mrg_ml[split][0], uint32_t(t), mm);
+            st_dsmem_f32(&mrg_ml[split][1], uint32_t(t), den);
         }
     }
-    // merge the 8 CTAs of the head through distributed shared memory: CTA s finishes dims [16 s, 16 s + 16)
+    // ONE cluster barrier: after it every partial this CTA needs sits in its own shared memory, and nobody touches a
+    // sibling's shared memory any more (so CTAs may exit independently)
     cluster_arrive();
     cluster_wait();
     if (t < 16) {
         const int d = split * 16 + t;
-        float ms[ATT_SPLITS], ls[ATT_SPLITS], os[ATT_SPLITS];
-#pragma unroll
-        for (int r = 0; r < ATT_SPLITS; ++r) {
-            ms[r] = ld_dsmem_f32(&cta_ml[0], uint32_t(r));
-            ls[r] = ld_dsmem_f32(&cta_ml[1], uint32_t(r));
-            os[r] = ld_dsmem_f32(&cta_o[d], uint32_t(r));
-        }
         float mm = -INFINITY;
 #pragma unroll
         for (int r = 0; r < ATT_SPLITS; ++r)
-            mm = fmaxf(mm, ms[r]);
+            mm = fmaxf(mm, mrg_ml[r][0]);
         float num = 0.f, den = 0.f;
 #pragma unroll
         for (int r = 0; r < ATT_SPLITS; ++r) {
-            const float w = (ms[r] == -INFINITY) ? 0.f : __expf(ms[r] - mm);
-            num = fmaf(w, os[r], num);
-            den = fmaf(w, ls[r], den);
+            const float mr = mrg_ml[r][0];
+            const float w  = (mr == -INFINITY) ? 0.f : __expf(mr - mm);
+            num = fmaf(w, mrg_o[r][t], num);
+            den = fmaf(w, mrg_ml[r][1], den);
         }
         const __half o = __float2half_rn(num / den);
         if (ao.out != nullptr) {
@@ -428,9 +451,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
                 ll_push_word(ao.push, (head * ATT_D + d) >> 1, mine | (other << 16));
         }
     }
-    // nobody may leave while a sibling still reads its shared memory
-    cluster_arrive();
-    cluster_wait();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

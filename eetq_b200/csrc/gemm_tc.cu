@@ -109,6 +109,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// Every wait in this kernel is followed by warp-collective `.sync.aligned` instructions (tcgen05.st / tcgen05.ld / tcgen05.wait)
+// or by an elected-lane issue.  Lanes leave the try_wait spin loop on different iterations whenever the wait really blocks, and
+// nothing re-converges them by itself: a tcgen05.st.sync.aligned executed by a partial warp silently drops lanes (seen as single
+// wrong feature rows, only in the MMA-bound regime where the dequant warps block on `aempty`).  So: wait, then re-converge.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity)
+{
+    mbar_wait(bar, parity);
+    __syncwarp();
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -537,7 +546,7 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
             for (int st = sg.s0; st < sg.s1; ++st, ++wcount) {
                 const int ws       = wcount % WS;
                 const uint32_t wph = (wcount / WS) & 1;
-                mbar_wait(wempty_bar + 8 * ws, wph ^ 1);
+                mbar_wait_warp(wempty_bar + 8 * ws, wph ^ 1);
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(wfull_bar + 8 * ws, W_STAGE);
                     // k beyond K (last stage when K % 256 != 0) is zero-filled by TMA; the matching activations are
@@ -564,7 +573,7 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
                 for (int xi = 0; xi < XSTEPS; ++xi, ++xcount) {
                     const int xs       = xcount % XS;
                     const uint32_t xph = (xcount / XS) & 1;
-                    mbar_wait(xempty_bar + 8 * xs, xph ^ 1);
+                    mbar_wait_warp(xempty_bar + 8 * xs, xph ^ 1);
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(xfull_bar + 8 * xs, X_STAGE);
 #pragma unroll
@@ -584,20 +593,20 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
         for (int u = u0; u < u1; ++seg) {
             const Segment sg = segment_at(p, u, u1);
             const int d      = seg % ND;
-            mbar_wait(tempty_bar + 8 * d, ((seg / ND) & 1) ^ 1);  // the epilogue has drained this accumulator
+            mbar_wait_warp(tempty_bar + 8 * d, ((seg / ND) & 1) ^ 1);  // the epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_addr = tmem_base + uint32_t(d * BT);
             for (int st = sg.s0; st < sg.s1; ++st, ++acount) {
                 const int a        = acount % A_STAGES;
                 const uint32_t aph = (acount / A_STAGES) & 1;
-                mbar_wait(afull_bar + 8 * a, aph);  // 256 k of dequantised weights sit in TMEM
+                mbar_wait_warp(afull_bar + 8 * a, aph);  // 256 k of dequantised weights sit in TMEM
                 tc_fence_after();
                 const uint32_t a_addr = tmem_base + uint32_t(A_COL0 + a * A_STAGE_COLS);
 #pragma unroll 1
                 for (int xi = 0; xi < XSTEPS; ++xi, ++xcount) {
                     const int xs       = xcount % XS;
                     const uint32_t xph = (xcount / XS) & 1;
-                    mbar_wait(xfull_bar + 8 * xs, xph);  // activation boxes landed
+                    mbar_wait_warp(xfull_bar + 8 * xs, xph);  // activation boxes landed
                     tc_fence_after();
                     if (elect_one_sync()) {
 #pragma unroll
@@ -658,26 +667,41 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
                     const uint32_t wph = (wcount / WS) & 1;
                     const int a        = acount % A_STAGES;
                     const uint32_t aph = (acount / A_STAGES) & 1;
-                    mbar_wait(wfull_bar + 8 * ws, wph);  // int8 stage landed
+                    mbar_wait_warp(wfull_bar + 8 * ws, wph);  // int8 stage landed
                     const uint32_t rp = w8_base + ws * W_STAGE + row_off;
                     uint4 in[CH];
 #pragma unroll
                     for (int j = 0; j < CH; ++j)
                         in[j] = lds128(rp + ((((cb + j) ^ (row & 7))) << 4));  // 128B swizzle: chunk ^ (row & 7)
+                    // Convert BEFORE releasing the weight stage and before waiting for the TMEM stage: (1) the stage may only be handed
+                    // back to TMA once the loads have RETURNED, not merely been issued (an mbarrier arrive does not wait for outstanding
+                    // shared-memory loads; the conversion consumes them), (2) in the MMA-bound regime the arithmetic then overlaps the
+                    // wait for `aempty` and only the TMEM stores remain on the critical path.
+                    uint32_t o[CH / 4][32];
+#pragma unroll
+                    for (int h = 0; h < CH / 4; ++h) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dequant16<T>(in[h * 4 + j], scale2, &o[h][8 * j]);
+                    }
+                    // pin the converted values here: the release below must not be scheduled ahead of the loads' consumers
+#pragma unroll
+                    for (int h = 0; h < CH / 4; ++h) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            asm volatile("mov.b32 %0, %0;" : "+r"(o[h][j])::"memory");
+                    }
+                    // generic-proxy reads of the stage are ordered before the async-proxy (TMA) writes that follow the release
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0)
                         mbar_arrive(wempty_bar + 8 * ws);
-                    mbar_wait(aempty_bar + 8 * a, aph ^ 1);  // the MMAs that read this A stage have completed
+                    mbar_wait_warp(aempty_bar + 8 * a, aph ^ 1);  // the MMAs that read this A stage have completed
                     tc_fence_after();
                     const uint32_t a_col = uint32_t(A_COL0 + a * A_STAGE_COLS + c_first * 8);
 #pragma unroll
-                    for (int h = 0; h < CH / 4; ++h) {
-                        uint32_t o[32];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dequant16<T>(in[h * 4 + j], scale2, &o[8 * j]);
-                        tmem_st_x32(tmem_base + lane_addr + a_col + uint32_t(h * 32), o);
-                    }
+                    for (int h = 0; h < CH / 4; ++h)
+                        tmem_st_x32(tmem_base + lane_addr + a_col + uint32_t(h * 32), o[h]);
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -703,7 +727,7 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
                 const bool fixup       = sg.s0 == 0 && sg.s1 < p.spt;
                 if (fixup)
                     break;  // always the last segment: handled jointly below
-                mbar_wait(tfull_bar + 8 * d, (seg / ND) & 1);
+                mbar_wait_warp(tfull_bar + 8 * d, (seg / ND) & 1);
                 tc_fence_after();
                 if constexpr (TRACE) {
                     if (et == 0 && seg < 4) tr[32 + 2 * seg] = clk64();
@@ -745,7 +769,7 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
                 while (ld_acquire_gpu(p.flags + g + jt) == 0) {
                 }
             }
-            mbar_wait(tfull_bar + 8 * d, (seg / ND) & 1);
+            mbar_wait_warp(tfull_bar + 8 * d, (seg / ND) & 1);
             tc_fence_after();
             joint_bar_sync<JOINT_THREADS>();
             if constexpr (TRACE) {

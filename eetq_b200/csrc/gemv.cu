@@ -121,10 +121,8 @@ struct XSlice<__half> {
         return s;
     }
     // RMSNorm in place, HF Llama arithmetic: fp16( fp16(x_f32 * r) * w )
-    __device__ __forceinline__ void apply_norm(float r, const __half* nw)
+    __device__ __forceinline__ void apply_norm(float r, const uint4& a, const uint4& b)
     {
-        const uint4 a = *reinterpret_cast<const uint4*>(nw);
-        const uint4 b = *reinterpret_cast<const uint4*>(nw + 8);
         const uint32_t wr[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -200,8 +198,10 @@ struct XSlice<__nv_bfloat16> {
         return s;
     }
     static __device__ __forceinline__ float rb(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-    __device__ __forceinline__ void apply_norm(float r, const __nv_bfloat16* nw)
+    __device__ __forceinline__ void apply_norm(float r, const uint4& a, const uint4& b)
     {
+        const uint32_t wr[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(wr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             f2[j].x = rb(rb(f2[j].x * r) * __bfloat162float(nw[2 * j]));
@@ -327,6 +327,11 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
     const int nrows     = row_end - row_begin;
     const int ngroups   = (nrows + R - 1) / R;
 
+    const int nelem      = pairs ? nrows / 2 : nrows;        // output elements produced by this CTA
+    const int elem_begin = pairs ? row_begin / 2 : row_begin;
+    float pre_s0 = 0.f, pre_s1 = 0.f, pre_bias = 0.f, pre_res = 0.f;  // M == 1, register-resident path: fetched ahead of the main loop
+    (void)pre_s1; (void)pre_bias; (void)pre_res;
+
     // let the next kernel in the stream start its own prologue (no-op without PDL)
     pdl_launch_dependents();
 
@@ -364,7 +369,38 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
             load_group(wb[0], 0);
         if (ngroups > 1)
             load_group(wb[1], 1);
+        // so do all other parameters: the scale(s) / bias of the output element this thread will finish (M == 1: element `tid`),
+        // and the RMSNorm weights of its activation chunks -- nothing static is left to fetch on the dependent path
+        if constexpr (M == 1) {
+            if (tid < nelem) {
+                if (pairs) {
+                    pre_s0 = to_float(scales[row_begin + 2 * tid]);
+                    pre_s1 = to_float(scales[row_begin + 2 * tid + 1]);
+                }
+                else {
+                    pre_s0 = to_float(scales[row_begin + tid]);
+                    if (bias != nullptr)
+                        pre_bias = to_float(bias[row_begin + tid]);
+                }
+            }
+        }
+        uint4 nw[KITERS][2];
+        if (fuse.xmode == GEMV_X_RMSNORM) {
+#pragma unroll
+            for (int i = 0; i < KITERS; ++i) {
+                const int c = tid + i * kThreads;
+                if (c < nchunks) {
+                    nw[i][0] = *reinterpret_cast<const uint4*>(fuse.norm_weight + int64_t(c) * 16);
+                    nw[i][1] = *reinterpret_cast<const uint4*>(fuse.norm_weight + int64_t(c) * 16 + 8);
+                }
+            }
+        }
         pdl_wait_prior_grids();
+        // the residual of this thread's output element travels together with the activations
+        if constexpr (M == 1) {
+            if (fuse.residual != nullptr && fuse.res_ll.tag_base == nullptr && tid < nelem)
+                pre_res = to_float(fuse.residual[elem_begin + tid]);
+        }
 
         XSlice<T> xs[M][KITERS];
         float xoff[M];
@@ -422,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
                 for (int i = 0; i < KITERS; ++i) {
                     const int c = tid + i * kThreads;
                     if (c < nchunks)
-                        xs[m][i].apply_norm(r, fuse.norm_weight + int64_t(c) * 16);
+                        xs[m][i].apply_norm(r, nw[i][0], nw[i][1]);
                 }
             }
         }
@@ -511,8 +547,6 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
             s += gemv_partial[(r * M + m) * kWarps + wi];
         return s * to_float(scales[row_begin + r]);
     };
-    const int nelem      = pairs ? nrows / 2 : nrows;        // output elements produced by this CTA
-    const int elem_begin = pairs ? row_begin / 2 : row_begin;
     auto out_value = [&](int e, int m) -> T {
         T o;
         if (pairs) {
@@ -543,6 +577,38 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
         }
         return o;
     };
+    if constexpr (M == 1 && XREG) {
+        // every operand of the tail is already in registers: partial sums -> scale (+bias) [-> SiLU * up] (+residual) -> store
+        auto raw = [&](int r) -> float {
+            float a = 0.f;
+#pragma unroll
+            for (int wi = 0; wi < kWarps; ++wi)
+                a += gemv_partial[r * kWarps + wi];
+            return a;
+        };
+        const bool plain_res = fuse.residual != nullptr && fuse.res_ll.tag_base == nullptr;
+        if (!ll_out && (fuse.residual == nullptr || plain_res)) {
+            if (tid < nelem) {
+                T o;
+                if (pairs) {
+                    const T g16    = from_float<T>(raw(2 * tid) * pre_s0);
+                    const T u16    = from_float<T>(raw(2 * tid + 1) * pre_s1);
+                    const float gf = to_float(g16);
+                    o = from_float<T>(to_float(from_float<T>(gf / (1.f + __expf(-gf)))) * to_float(u16));
+                }
+                else {
+                    float out = raw(tid) * pre_s0;
+                    if (bias != nullptr)
+                        out += pre_bias;
+                    o = from_float<T>(out);
+                }
+                if (plain_res)
+                    o = from_float<T>(to_float(o) + pre_res);
+                y[elem_begin + tid] = o;
+            }
+            return;
+        }
+    }
     if constexpr (M == 1 && DTypeOf<T>::value == EETQ_B200_F16) {
         if (ll_out) {
             for (int wd = tid; wd < nelem / 2; wd += kThreads) {
