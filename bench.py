@@ -213,7 +213,7 @@ def run_reference(args):
         "note": "the reference has no CPU forward and its GPU kernels refuse sm>=90; this is the north-star CPU path "
                 "(EETQ-style dequantise -> torch.matmul, examples/layers/test_w8a16_gemm.py:44-47) via oracle/w8a16_oracle.py",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -231,8 +231,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     s = shape_of(args)
     ctx_max = args.prompt + args.steps + args.warmup + 64
@@ -436,7 +434,7 @@ def run_ours(args):
             "tokens_match_single_gpu": tokens_match,
             "prefill_ms": prefill_ms, "prefill_cold_ms": prefill_cold_ms, "build_s": t_build, "quantize_s": t_quant,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # tearing down NCCL while CUDA graphs that captured collectives are alive can hang: flush and leave
         torch.cuda.synchronize()
@@ -446,8 +444,27 @@ def run_ours(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one), so file
+    descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

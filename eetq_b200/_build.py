@@ -23,6 +23,9 @@ NVCC_FLAGS = [
 ]
 if os.environ.get("EETQ_B200_BUILD_V1") == "1":
     NVCC_FLAGS.append("-DEETQ_B200_WITH_V1")
+# development only: EETQ_B200_BUILD_TRACE=1 compiles the in-situ timeline recorder into the decode kernels (tools/timeline.py)
+if os.environ.get("EETQ_B200_BUILD_TRACE") == "1":
+    NVCC_FLAGS.append("-DEETQ_B200_TRACE")
 
 
 def _nvcc() -> str:

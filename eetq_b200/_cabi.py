@@ -11,7 +11,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeetq_b200.so")
+# EETQ_B200_LIB: development override (e.g. the timeline build, tools/timeline.py); the product always loads the in-tree library
+LIB_PATH = os.environ.get("EETQ_B200_LIB") or os.path.join(_HERE, "libeetq_b200.so")
 
 F16, BF16, F32 = 0, 1, 2
 FLAG_DEFAULT, FLAG_FORCE_GEMV, FLAG_FORCE_TC, FLAG_PDL = 0, 1, 2, 4
@@ -35,7 +36,8 @@ class GemvOpts(ctypes.Structure):
     """eetq_b200_gemv_opts"""
     _fields_ = [("norm_weight", ctypes.c_void_p), ("eps", ctypes.c_float), ("xmode", ctypes.c_int), ("epi", ctypes.c_int),
                 ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int64), ("x_ll", ctypes.POINTER(LL)), ("residual_ll", ctypes.POINTER(LL)),
-                ("residual_off", ctypes.c_int64), ("push", ctypes.POINTER(LLPush))]
+                ("residual_off", ctypes.c_int64), ("push", ctypes.POINTER(LLPush)), ("next_w", ctypes.c_void_p),
+                ("next_n", ctypes.c_int64), ("next_k", ctypes.c_int64)]
 
 
 _c_i64 = ctypes.c_int64
@@ -62,6 +64,7 @@ SIGNATURES = {
     "eetq_b200_w8a16_gemm_trace": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_sz, _c_vp, _c_sz,
                                             _c_vp]),
     "eetq_b200_w8a16_gemm_trace_info": (_c_int, [_c_i64, _c_i64, _c_i64, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)]),
+    "eetq_b200_set_timeline": (_c_int, [_c_vp, ctypes.c_uint64]),
     "eetq_b200_w8a16_gemm_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int,
                                            _c_vp, _c_sz, _c_vp]),
     "eetq_b200_w8a16_gemv_fused": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int,
@@ -73,7 +76,7 @@ SIGNATURES = {
     "eetq_b200_prefill_rope_kv": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp]),
     "eetq_b200_silu_mul": (_c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp]),
     "eetq_b200_decode_attention": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, ctypes.POINTER(LLPush),
-                                            _c_int, _c_vp]),
+                                            _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
     "eetq_b200_lm_head_scratch_bytes": (_c_sz, []),
     "eetq_b200_lm_head_argmax": (_c_int, [_c_vp, ctypes.POINTER(LL), _c_vp, ctypes.c_float, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp,
                                           _c_vp, _c_vp, ctypes.POINTER(LLPush), _c_int, _c_int, _c_vp]),

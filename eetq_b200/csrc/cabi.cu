@@ -269,6 +269,14 @@ int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200,
     ex.epi         = o->epi;
     ex.residual    = o->residual;
     ex.ldr         = o->ldr;
+    if (o->next_w != nullptr) {
+        EB_CHECK_ARG(aligned16(o->next_w), "w8a16_gemv_fused: next_w must be 16-byte aligned");
+        if (int rc = check_kn("w8a16_gemv_fused (next_w)", o->next_k, o->next_n))
+            return rc;
+        ex.next_w = o->next_w;
+        ex.next_n = o->next_n;
+        ex.next_k = o->next_k;
+    }
     if (x_ll) {
         ex.x_ll.tag_base = static_cast<const int*>(o->x_ll->step);
         ex.x_ll.per_step = o->x_ll->per_step;
@@ -335,6 +343,19 @@ int eetq_b200_w8a16_gemm(const void* x, const int8_t* w_b200, const void* scales
 {
     return eetq_b200_w8a16_gemm_ex(x, K, w_b200, scales, bias, y, N, M, N, K, dtype, workspace, workspace_bytes,
                                    EETQ_B200_FLAG_DEFAULT, stream);
+}
+
+// Development aid (trace builds only; a no-op otherwise): point the kernels' timeline recorder at a device buffer of
+// 2 + 2 * capacity 64-bit words ([0] = record count, zero it before use).  Returns 1 when the library records, else 0.
+int eetq_b200_set_timeline(void* buffer, uint64_t capacity)
+{
+    trace_set_gemv(buffer, static_cast<unsigned int>(capacity));
+    trace_set_decode(buffer, static_cast<unsigned int>(capacity));
+#ifdef EETQ_B200_TRACE
+    return 1;
+#else
+    return 0;
+#endif
 }
 
 int eetq_b200_w8a16_gemm_host(const void* x_host, void* x_dev, const int8_t* w_b200, const void* scales,

@@ -12,6 +12,8 @@
 // one 8-byte store straight into every peer's copy over NVLink (symmetric memory).  A word is valid when its tag equals the
 // tag of the exchange (step counter x exchanges per step + exchange index), so data and flag arrive together: no fence, no
 // separate flag, no collective call, and the consumer's prologue simply polls the words it is about to use.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eetq_b200 {
@@ -51,7 +53,9 @@ __global__ void __launch_bounds__(256) embed_kernel(const __half* __restrict__ t
     // The embedding is the FIRST kernel of a decode step.  It releases its dependents only after the previous step's last
     // kernel (lm_head + arg-max, which advances *pos and the step counter) has completed, so every later kernel of this step
     // may read the position before its own dependency wait.
+    trace_ev(TRACE_EMBED, 0);
     pdl_wait_prior_grids();
+    trace_ev(TRACE_EMBED, 2);
     pdl_launch_dependents();
     const int64_t t = *token;
     if (ll.tag_base == nullptr) {
@@ -254,6 +258,7 @@ __device__ __forceinline__ void st_dsmem_f32(float* local_ptr, uint32_t rank, fl
 struct AttnOut {
     __half* out;       // plain output [heads_local * 128] (world == 1) or nullptr
     LLPush push;       // LL output: every rank's attention vector, this rank's heads at element offset push.elem_off
+    NextHint next;     // w != nullptr: the GEMV that consumes the attention output; its per-CTA head rows are requested into L2
 };
 
 __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cos_t,
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     const int head    = blockIdx.x;
     const int split   = int(cluster_ctarank());  // == blockIdx.y
 
+    trace_ev(TRACE_ATTN, 0);
     pdl_launch_dependents();
     cluster_arrive_relaxed();  // "I am running": matched by the wait just before the first remote shared-memory store
     const __half* kbase = kcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
@@ -298,6 +304,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     // need neither `pos` nor anything the preceding kernel produces.
     load_chunk(kreg0, vreg0, split);
     load_chunk(kreg1, vreg1, split + ATT_SPLITS);
+    // the attention stream is small (the layer's KV rows): use the idle HBM time to pull the head rows of the next GEMV into L2
+    if (ao.next.w != nullptr && t == ATT_THREADS - 32)
+        l2_prefetch_next(ao.next, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
     // *pos was advanced by the PREVIOUS step's last kernel, which completed before this step's first kernel released its
     // dependents (embed_kernel): the position and its rotary row can be fetched ahead of the dependency wait as well
     const int pos = *pos_p;
@@ -306,7 +315,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
         rope_c = __half2float(cos_t[int64_t(pos) * (ATT_D / 2) + t]);
         rope_s = __half2float(sin_t[int64_t(pos) * (ATT_D / 2) + t]);
     }
+    trace_ev(TRACE_ATTN, 1);
     pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
+    trace_ev(TRACE_ATTN, 2);
     const int new_chunk = pos / ATT_ROWS;
     const bool owns_new = (new_chunk % ATT_SPLITS) == split;
 
@@ -335,6 +346,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
 #pragma unroll
     for (int d = 0; d < 8; ++d)
         qf[d] = q_s[sub * 8 + d];
+    trace_ev(TRACE_ATTN, 3);
 
     // online softmax state of this 16-lane group (identical in all 16 lanes; each lane owns 8 dims of the numerator)
     float m_run = -INFINITY, l_run = 0.f;
@@ -390,6 +402,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
             load_chunk(kreg1, vreg1, chunk + 3 * ATT_SPLITS);
     }
 
+    trace_ev(TRACE_ATTN, 4);
     // merge the 8 groups of this CTA
 #pragma unroll
     for (int d = 0; d < 8; ++d)
@@ -425,6 +438,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     // sibling's shared memory any more (so CTAs may exit independently)
     cluster_arrive();
     cluster_wait();
+    trace_ev(TRACE_ATTN, 5);
     if (t < 16) {
         const int d = split * 16 + t;
         float mm = -INFINITY;
@@ -451,6 +465,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
                 ll_push_word(ao.push, (head * ATT_D + d) >> 1, mine | (other << 16));
         }
     }
+    trace_ev(TRACE_ATTN, 6);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -497,6 +512,7 @@ __global__ void __launch_bounds__(LM_THREADS, 2) lm_head_argmax_kernel(const LmA
     const int nrows     = row_end - row_begin;
     const int ngroups   = (nrows + LM_R - 1) / LM_R;
 
+    trace_ev(TRACE_LMHEAD, 0);
     pdl_launch_dependents();
     uint4 wb[2][LM_R][KITERS];
     auto load_group = [&](uint4 (&buf)[LM_R][KITERS], int g) {
@@ -513,7 +529,9 @@ __global__ void __launch_bounds__(LM_THREADS, 2) lm_head_argmax_kernel(const LmA
     };
     if (ngroups > 0) load_group(wb[0], 0);
     if (ngroups > 1) load_group(wb[1], 1);
+    trace_ev(TRACE_LMHEAD, 1);
     pdl_wait_prior_grids();
+    trace_ev(TRACE_LMHEAD, 2);
 
     // activation slice: 8 values per chunk, final RMSNorm applied in registers (HF arithmetic)
     uint32_t xh[KITERS][4];
@@ -707,6 +725,9 @@ __global__ void __launch_bounds__(LM_THREADS, 2) lm_head_argmax_kernel(const LmA
 }
 
 }  // namespace
+
+EB_TRACE_SETTER(trace_set_decode)
+
 }  // namespace eetq_b200
 
 using namespace eetq_b200;
@@ -822,8 +843,10 @@ int eetq_b200_silu_mul(const void* gu, int64_t ldg, void* act, int64_t lda, int6
 //   (head-major); out [H_local] plain fp16, or NULL with `push` describing the LL exchange of the full attention vector.
 int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
                                void* vcache, void* out, int64_t H_local, int64_t D, int64_t max_ctx, const eetq_b200_ll_push* push,
-                               int pdl, void* stream)
+                               const void* next_w, int64_t next_n, int64_t next_k, int pdl, void* stream)
 {
+    EB_CHECK_ARG(next_w == nullptr || ((reinterpret_cast<uintptr_t>(next_w) & 15u) == 0 && next_n > 0 && next_k > 0 && next_k % 64 == 0),
+                 "decode_attention: bad next_w hint");
     EB_CHECK_ARG(qkv && cos_t && sin_t && pos_i32 && kcache && vcache, "decode_attention: null pointer argument");
     EB_CHECK_ARG((out != nullptr) != (push != nullptr), "decode_attention: exactly one of out / push must be given");
     EB_CHECK_ARG(D == ATT_D && H_local % D == 0 && H_local > 0, "decode_attention: head_dim must be 128");
@@ -834,6 +857,12 @@ int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* s
         EB_CHECK_ARG(push->world >= 1 && push->world <= 8 && push->step != nullptr && push->peers != nullptr, "decode_attention: bad LL push");
         fill_push(ao.push, push->world, push->peers, push->local, push->elem_off, push->step, push->per_step, push->index);
     }
+    static const bool l2_next = [] {
+        const char* e = getenv("EETQ_B200_L2_NEXT");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    if (l2_next && next_w != nullptr)
+        ao.next = make_next_hint(next_w, next_n, next_k);
     const int heads = int(H_local / D);
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];

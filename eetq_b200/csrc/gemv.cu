@@ -33,6 +33,8 @@
 // The TMA-ring and chained-launch variants of round 1 (measured slower) were removed.
 //
 // Algorithmic bytes per call: K*N + 2*N + 2*M*K + 2*M*N; each weight byte is read exactly once.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eetq_b200 {
@@ -303,6 +305,7 @@ struct GemvFuse {
     LLTag res_ll;   // tag_base != nullptr: residual points at LL words of the full output vector; element offset res_off
     int res_off;
     LLPush push;    // world > 0: outputs are pushed as LL words to every rank instead of being stored to y
+    NextHint next;  // w != nullptr: ask L2 for the next GEMV's per-CTA head rows when this CTA leaves its main loop
 };
 
 template <typename T, int M, int KITERS, int R, bool XREG>
@@ -332,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
     float pre_s0 = 0.f, pre_s1 = 0.f, pre_bias = 0.f, pre_res = 0.f;  // M == 1, register-resident path: fetched ahead of the main loop
     (void)pre_s1; (void)pre_bias; (void)pre_res;
 
+    trace_ev(TRACE_GEMV, 0);
     // let the next kernel in the stream start its own prologue (no-op without PDL)
     pdl_launch_dependents();
 
@@ -369,6 +373,11 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
             load_group(wb[0], 0);
         if (ngroups > 1)
             load_group(wb[1], 1);
+        // L2 staging for the NEXT GEMV (see GemvExtras::next_w).  Measured alternatives, all slower than no hint: staging the rest of
+        // this CTA's OWN slice (10.9 vs 9.8 us per launch), staging a few rows for EVERY CTA of the next kernel (571 vs 589 tok/s),
+        // requesting when the CTA leaves its main loop instead of here (548 vs 583 tok/s).
+        if (fuse.next.w != nullptr && tid == kThreads - 32)
+            l2_prefetch_next(fuse.next, blockIdx.x, gridDim.x);
         // so do all other parameters: the scale(s) / bias of the output element this thread will finish (M == 1: element `tid`),
         // and the RMSNorm weights of its activation chunks -- nothing static is left to fetch on the dependent path
         if constexpr (M == 1) {
@@ -395,7 +404,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
                 }
             }
         }
+        trace_ev(TRACE_GEMV, 1);
         pdl_wait_prior_grids();
+        trace_ev(TRACE_GEMV, 2);
         // the residual of this thread's output element travels together with the activations
         if constexpr (M == 1) {
             if (fuse.residual != nullptr && fuse.res_ll.tag_base == nullptr && tid < nelem)
@@ -471,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
             xoff[m] = -XSlice<T>::kOffset * so;
         }
 
+        trace_ev(TRACE_GEMV, 3);
         auto compute_group = [&](uint4 (&buf)[R][KITERS], int g) {
             float acc[M][R];
 #pragma unroll
@@ -537,6 +549,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
         }
     }
 
+    trace_ev(TRACE_GEMV, 4);
     __syncthreads();
     // epilogue: cross-warp sum, per-channel scale (+bias), optional SiLU(gate)*up over row pairs, optional residual, then a
     // plain store or an LL push to every rank
@@ -606,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
                     o = from_float<T>(to_float(o) + pre_res);
                 y[elem_begin + tid] = o;
             }
+            trace_ev(TRACE_GEMV, 5);
             return;
         }
     }
@@ -626,6 +640,18 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
     }
 }
 
+// launch geometry shared by launch_variant and make_next_hint
+int gemv_grid(int sm_count, int ctas_per_sm, int N, int align)
+{
+    constexpr int kMaxRows = 96;  // rows per CTA bound (sizes the partial-sum buffer)
+    int grid = sm_count * ctas_per_sm;
+    while ((N + grid - 1) / grid + align > kMaxRows)  // keep rows/CTA <= kMaxRows, and grid a multiple of the SM count
+        grid += sm_count;
+    if (grid > N / align)
+        grid = N / align;
+    return grid;
+}
+
 template <typename T, int M, int KITERS, int R, bool XREG>
 int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N,
                    int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
@@ -636,14 +662,8 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
         return EETQ_B200_ECUDA;
     }
     constexpr int kCtasPerSm = min_ctas(M, KITERS, XREG);
-    constexpr int kMaxRows   = 96;  // rows per CTA bound (sizes the partial-sum buffer)
     const int align          = (fuse.epi == GEMV_EPI_SILU_PAIRS ? 2 : 1) * (fuse.push.world > 0 ? 2 : 1);
-    int grid                 = di.sm_count * kCtasPerSm;
-    // keep rows/CTA <= kMaxRows, and grid a multiple of the SM count
-    while ((N + grid - 1) / grid + align > kMaxRows)
-        grid += di.sm_count;
-    if (grid > N / align)
-        grid = N / align;
+    const int grid           = gemv_grid(di.sm_count, kCtasPerSm, N, align);
     const int max_rows = (N + grid - 1) / grid + align;
     const int padded   = ((max_rows + R - 1) / R) * R;  // the partial buffer is indexed by padded group rows
     const size_t smem  = size_t(padded) * M * kWarps * sizeof(float);
@@ -728,10 +748,33 @@ GemvFuse<T> make_fuse(const GemvExtras& ex)
     f.res_ll      = ex.res_ll;
     f.res_off     = ex.res_off;
     f.push        = ex.push;
+    static const bool l2_next = [] {
+        const char* e = getenv("EETQ_B200_L2_NEXT");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    if (l2_next && ex.next_w != nullptr)
+        f.next = make_next_hint(ex.next_w, ex.next_n, ex.next_k);
     return f;
 }
 
 }  // namespace
+
+EB_TRACE_SETTER(trace_set_gemv)
+
+NextHint make_next_hint(const void* w, int64_t N, int64_t K)
+{
+    NextHint h;
+    if (w == nullptr || N <= 0 || K <= 0)
+        return h;
+    // measured flat between 6 and 24 MB; >= 48 MB evicts the current kernel's own stream from L2
+    static const long long budget = [] {
+        const char* e = getenv("EETQ_B200_L2_NEXT_MB");
+        return static_cast<long long>((e != nullptr && e[0] != '\0') ? atoi(e) : 12) << 20;
+    }();
+    h.w     = static_cast<const uint8_t*>(w);
+    h.bytes = (N * K < budget ? N * K : budget) & ~15ll;
+    return h;
+}
 
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
                 int M, int64_t N, int64_t K, int dtype, const GemvExtras& ex, bool pdl, cudaStream_t stream)

@@ -324,7 +324,8 @@ class W8A16LlamaDecoder:
 
         dist.all_gather_into_tensor(full, part, group=self.group)
 
-    def _gemv(self, x, ldx, lin: _Shard, y, *, norm_w=None, xmode=0, epi=0, residual=None, x_tag=None, res_tag=None, res_off=0, push=None):
+    def _gemv(self, x, ldx, lin: _Shard, y, *, norm_w=None, xmode=0, epi=0, residual=None, x_tag=None, res_tag=None, res_off=0, push=None,
+              nxt: Optional["_Shard"] = None):
         """One fused decode GEMV over this rank's rows.  x / residual: tensors (plain) or raw LL addresses (int) with their tags."""
         o = _cabi.GemvOpts()
         o.norm_weight = 0 if norm_w is None else norm_w.data_ptr()
@@ -335,6 +336,8 @@ class W8A16LlamaDecoder:
         o.residual_ll = ctypes.pointer(res_tag) if res_tag is not None else None
         o.residual_off = res_off
         o.push = ctypes.pointer(push) if push is not None else None
+        if nxt is not None:  # L2 staging hint: the GEMV that runs next (eetq_b200_gemv_opts.next_w)
+            o.next_w, o.next_n, o.next_k = nxt.w.data_ptr(), nxt.N, nxt.K
         xp = ctypes.c_void_p(x if isinstance(x, int) else x.data_ptr())
         rc = self._L.eetq_b200_w8a16_gemv_fused(xp, ldx, _vp(lin.w), _vp(lin.scales), None, _vp(y), lin.N, 1, lin.N, lin.K, _cabi.F16,
                                                 ctypes.byref(o), 1 if self.pdl else 0, self._stream())
@@ -365,35 +368,39 @@ class W8A16LlamaDecoder:
                 self._gemv(x_in, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1, x_tag=x_tag)
                 push = self._push("attn", plan["heads"][0] * D, plan["attn"](li))
                 _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
-                                                         _vp(self.vcache[li]), None, self.Hl, D, self.max_ctx, ctypes.byref(push), pdl, st()),
+                                                         _vp(self.vcache[li]), None, self.Hl, D, self.max_ctx, ctypes.byref(push),
+                                                         _vp(w["o"].w), w["o"].N, w["o"].K, pdl, st()),
                             "decode_attention")
                 # x2 = x + o_proj(attn)
+                nxt_qkv = self.layers[li + 1]["qkv"] if li + 1 < len(self.layers) else None
                 self._gemv(self._ll_local("attn"), H, w["o"], None, x_tag=self._tag(plan["attn"](li)), residual=x_in, res_tag=x_tag, res_off=n0,
-                           push=self._push("x2", n0, plan["x2"](li)))
+                           push=self._push("x2", n0, plan["x2"](li)), nxt=w["gu"])
                 # act = silu(gate(norm(x2))) * up(norm(x2))
                 x2_tag = self._tag(plan["x2"](li))
                 self._gemv(self._ll_local("x2"), H, w["gu"], None, norm_w=w["ln2"], xmode=1, epi=1, x_tag=x2_tag,
-                           push=self._push("act", i0, plan["act"](li)))
+                           push=self._push("act", i0, plan["act"](li)), nxt=w["down"])
                 # x = x2 + down(act)
                 self._gemv(self._ll_local("act"), I, w["down"], None, x_tag=self._tag(plan["act"](li)), residual=self._ll_local("x2"),
-                           res_tag=x2_tag, res_off=n0, push=self._push("x", n0, plan["x_out"](li)))
+                           res_tag=x2_tag, res_off=n0, push=self._push("x", n0, plan["x_out"](li)), nxt=nxt_qkv)
             else:
+                nxt_qkv = self.layers[li + 1]["qkv"] if li + 1 < len(self.layers) else None
                 self._gemv(self.x, H, w["qkv"], self.qkv, norm_w=w["ln1"], xmode=1)
                 attn_out = self.attn[n0:n0 + self.Hl] if nccl else self.attn
                 _cabi.check(L.eetq_b200_decode_attention(_vp(self.qkv), _vp(self.cos), _vp(self.sin), _vp(self.pos), _vp(self.kcache[li]),
-                                                         _vp(self.vcache[li]), _vp(attn_out), self.Hl, D, self.max_ctx, None, pdl, st()),
+                                                         _vp(self.vcache[li]), _vp(attn_out), self.Hl, D, self.max_ctx, None,
+                                                         _vp(w["o"].w), w["o"].N, w["o"].K, pdl, st()),
                             "decode_attention")
                 if nccl:
                     self._all_gather(self.attn, attn_out)
                 sl = slice(n0, n0 + w["o"].N)
-                self._gemv(self.attn, H, w["o"], self.x2[sl], residual=self.x[sl])
+                self._gemv(self.attn, H, w["o"], self.x2[sl], residual=self.x[sl], nxt=w["gu"])
                 if nccl:
                     self._all_gather(self.x2, self.x2[sl])
                 al = slice(i0, i0 + self.Il)
-                self._gemv(self.x2, H, w["gu"], self.act[al], norm_w=w["ln2"], xmode=1, epi=1)
+                self._gemv(self.x2, H, w["gu"], self.act[al], norm_w=w["ln2"], xmode=1, epi=1, nxt=w["down"])
                 if nccl:
                     self._all_gather(self.act, self.act[al])
-                self._gemv(self.act, I, w["down"], self.x[sl], residual=self.x2[sl])
+                self._gemv(self.act, I, w["down"], self.x[sl], residual=self.x2[sl], nxt=nxt_qkv)
                 if nccl:
                     self._all_gather(self.x, self.x[sl])
 

@@ -138,6 +138,11 @@ int eetq_b200_w8a16_gemm_trace(const void* x, int64_t ldx, const int8_t* w_b200,
                                void* stream);
 int eetq_b200_w8a16_gemm_trace_info(int64_t M, int64_t N, int64_t K, int* grid, int* slots);
 
+/* Development aid: point the decode kernels' in-situ timeline recorder at a device buffer of (2 + 2 * capacity) 64-bit words
+ * ([0] = record count; zero the buffer first; records are {tag << 56 | block << 16 | event, %globaltimer ns}).  Only a library
+ * built with EETQ_B200_BUILD_TRACE=1 records; the product build ignores the call.  Returns 1 if recording is compiled in, else 0. */
+int eetq_b200_set_timeline(void* buffer, uint64_t capacity);
+
 /* Convenience for hosts without their own device-memory plumbing: x_host / y_host are HOST buffers
  * (pinned for true async); the call stages them through the caller-provided device scratch
  * x_dev [M*K], y_dev [M*N] on `stream` (H2D copy, kernel, D2H copy; no synchronisation). */
@@ -176,6 +181,9 @@ typedef struct eetq_b200_ll_push {   /* producer side */
 } eetq_b200_ll_push;
 
 /* eetq_b200_w8a16_gemv_fused: the decode GEMV (M <= 8) with glue folded in (all fields optional / zero):
+ *   Every CTA requests its first two row groups into registers BEFORE the dependency wait (programmatic dependent launch); given
+ *   next_w, the grid also asks L2 (cp.async.bulk.prefetch.L2) for the head of the NEXT GEMV's weights, whose first CTAs then run out
+ *   of L2, finish early and let the kernel after them start its weight stream sooner.
  *   xmode 0: plain;  1: x := RMSNorm(x; norm_weight, eps) on load (HF LlamaRMSNorm arithmetic; replaces the reference's
  *   separate generalT5LayerNorm launch);  2: x := silu(x[:, :K]) * x[:, K:2K] (ldx >= 2K);
  *   epi 0: plain;  1: weight rows are interleaved (gate_0, up_0, gate_1, up_1, ...) and the kernel emits the N/2 values
@@ -195,6 +203,8 @@ typedef struct eetq_b200_gemv_opts {
     const eetq_b200_ll* residual_ll;
     int64_t residual_off;
     const eetq_b200_ll_push* push;
+    const void* next_w;              /* optional L2 staging hint: the b200 weight matrix [next_n rows][next_k bytes] of the decode GEMV */
+    int64_t next_n, next_k;          /* that runs next; this kernel asks L2 for the first megabytes of it (its first CTAs' slices) */
 } eetq_b200_gemv_opts;
 int eetq_b200_w8a16_gemv_fused(const void* x, int64_t ldx, const int8_t* w_b200, const void* scales, const void* bias, void* y,
                                int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, const eetq_b200_gemv_opts* opts, int pdl,
@@ -222,9 +232,12 @@ int eetq_b200_silu_mul(const void* gu, int64_t ldg, void* act, int64_t lda, int6
  * dependency wait; the 8 partial results of a head are merged through distributed shared memory.
  *   qkv [3 * H_local] = q | k | v raw projections of this rank's heads; cos/sin [max_pos][D/2]; kcache/vcache
  *   [H_local/D][max_ctx][D] head-major (row *pos of every head is written); out [H_local] plain fp16, or NULL and `push`
- *   describes the LL exchange of the full attention vector (elem_off = first element of this rank's heads). */
+ *   describes the LL exchange of the full attention vector (elem_off = first element of this rank's heads).
+ *   next_w / next_n / next_k (optional): the weight matrix of the GEMV that follows (o_proj); its head is requested into L2
+ *   while the attention itself leaves HBM mostly idle (see eetq_b200_gemv_opts.next_w). */
 int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* sin_t, const void* pos_i32, void* kcache,
                                void* vcache, void* out, int64_t H_local, int64_t D, int64_t max_ctx, const eetq_b200_ll_push* push,
+                               const void* next_w, int64_t next_n, int64_t next_k,
                                int pdl, void* stream);
 /* Final RMSNorm + fp16 lm_head (the reference leaves lm_head unquantised, quantizer.py:40) + greedy arg-max in ONE launch:
  *   logits[v] = RMSNorm(x; norm_w, eps) . W[v, :] over this rank's V_local vocabulary rows (global ids v_begin ..); the last CTA

@@ -112,7 +112,7 @@ def test_decode_attention_matches_fp32_reference(cuda, max_ctx, pos):
     knew = apply_rope(qkv[H:2 * H].view(1, heads, D), cos[pos:pos + 1], sin[pos:pos + 1])[0]
     kc_ref[:, pos] = knew
     vc_ref[:, pos] = qkv[2 * H:].view(heads, D)
-    rc = _cabi.lib().eetq_b200_decode_attention(vp(qkv), vp(cos), vp(sin), vp(pos_t), vp(kc), vp(vc), vp(out), H, D, max_ctx, None, 0, stream())
+    rc = _cabi.lib().eetq_b200_decode_attention(vp(qkv), vp(cos), vp(sin), vp(pos_t), vp(kc), vp(vc), vp(out), H, D, max_ctx, None, None, 0, 0, 0, stream())
     _cabi.check(rc, "decode_attention")
     torch.cuda.synchronize()
     ref = torch_attention_reference(qkv[:H].view(heads, D), kc_ref, vc_ref, cos, sin, pos).reshape(-1)
