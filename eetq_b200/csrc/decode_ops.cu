@@ -207,25 +207,34 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const __half* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ATT_D       = 128;
 constexpr int ATT_THREADS = 128;
-constexpr int ATT_ROWS    = 64;  // cache positions per chunk (8 per rowlane)
+constexpr int ATT_RMAX    = 10;  // cache rows per rowlane in one register buffer (a chunk = 8 rowlanes x rpl <= 80 positions)
 constexpr int ATT_SPLITS  = 8;   // CTAs per head == cluster size
 
-__device__ __forceinline__ float dot8(const uint4& kv, const float (&q)[8])
+// acc(fp32) += a(fp16) * b(fp16): one FHFMA on sm_100a (exact product, single fp32 rounding) -- no fp16 -> fp32 conversions
+__device__ __forceinline__ float fhfma(uint32_t a2, uint32_t b2, int hi, float acc)
 {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&kv.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&kv.y));
-    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&kv.z));
-    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&kv.w));
-    return q[0] * a.x + q[1] * a.y + q[2] * b.x + q[3] * b.y + q[4] * c.x + q[5] * c.y + q[6] * d.x + q[7] * d.y;
+    const uint16_t a = hi ? uint16_t(a2 >> 16) : uint16_t(a2 & 0xffffu);
+    const uint16_t b = hi ? uint16_t(b2 >> 16) : uint16_t(b2 & 0xffffu);
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(a), "h"(b));
+    return acc;
 }
-__device__ __forceinline__ void axpy8(float p, const uint4& vv, float (&acc)[8])
+// 8 fp16 cache values x 8 fp16 query values (packed pairs), fp32 accumulation, two independent chains
+__device__ __forceinline__ float dot8(const uint4& kv, const uint32_t (&q)[4])
 {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vv.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
-    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&vv.z));
-    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&vv.w));
-    acc[0] = fmaf(p, a.x, acc[0]); acc[1] = fmaf(p, a.y, acc[1]); acc[2] = fmaf(p, b.x, acc[2]); acc[3] = fmaf(p, b.y, acc[3]);
-    acc[4] = fmaf(p, c.x, acc[4]); acc[5] = fmaf(p, c.y, acc[5]); acc[6] = fmaf(p, d.x, acc[6]); acc[7] = fmaf(p, d.y, acc[7]);
+    float a = 0.f, b = 0.f;
+    a = fhfma(kv.x, q[0], 0, a); b = fhfma(kv.x, q[0], 1, b);
+    a = fhfma(kv.y, q[1], 0, a); b = fhfma(kv.y, q[1], 1, b);
+    a = fhfma(kv.z, q[2], 0, a); b = fhfma(kv.z, q[2], 1, b);
+    a = fhfma(kv.w, q[3], 0, a); b = fhfma(kv.w, q[3], 1, b);
+    return a + b;
+}
+// acc[0..7] += p * v[0..7], p as fp16 (the usual flash-attention choice for the P.V product), fp32 accumulation
+__device__ __forceinline__ void axpy8(uint32_t p2, const uint4& vv, float (&acc)[8])
+{
+    acc[0] = fhfma(vv.x, p2, 0, acc[0]); acc[1] = fhfma(vv.x >> 16, p2, 0, acc[1]);
+    acc[2] = fhfma(vv.y, p2, 0, acc[2]); acc[3] = fhfma(vv.y >> 16, p2, 0, acc[3]);
+    acc[4] = fhfma(vv.z, p2, 0, acc[4]); acc[5] = fhfma(vv.z >> 16, p2, 0, acc[5]);
+    acc[6] = fhfma(vv.w, p2, 0, acc[6]); acc[7] = fhfma(vv.w >> 16, p2, 0, acc[7]);
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -234,7 +243,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank()
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank)
@@ -247,12 +255,18 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t r
     return v;
 }
 
-__device__ __forceinline__ void st_dsmem_f32(float* local_ptr, uint32_t rank, float v)
+// Remote shared-memory store that also signals: writes v into CTA `rank`'s copy of *local_ptr and completes 4 transaction bytes on
+// that CTA's copy of *local_bar (st.async + mbarrier complete_tx) -- data and "it has arrived" travel together, so the receiver
+// waits on its own mbarrier and no cluster-wide barrier or release fence sits on the critical path.
+__device__ __forceinline__ void st_dsmem_f32_signal(float* local_ptr, unsigned long long* local_bar, uint32_t rank, float v)
 {
     const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr));
-    uint32_t ra;
+    const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(local_bar));
+    uint32_t ra, rb;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(b), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb)
+                 : "memory");
 }
 
 struct AttnOut {
@@ -266,13 +280,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
                                                                    __half* __restrict__ kcache, __half* __restrict__ vcache,
                                                                    int H, int max_ctx, float scale, const AttnOut ao)
 {
-    __shared__ float q_s[ATT_D];
+    __shared__ __align__(16) __half q_s[ATT_D];  // rotated query, fp16 (HF evaluates RoPE in the model dtype)
     __shared__ __align__(16) __half knew[ATT_D];
     __shared__ __align__(16) __half vnew[ATT_D];
     __shared__ float grp_o[8][ATT_D];   // per 16-lane group partial numerators
     __shared__ float grp_ml[8][2];      // per group (max, denominator)
     __shared__ float mrg_o[ATT_SPLITS][16];  // partial numerators of MY 16 output dims, one row pushed by every CTA of the cluster
     __shared__ float mrg_ml[ATT_SPLITS][2];  // (max, denominator) of every CTA of the cluster
+    __shared__ __align__(8) unsigned long long mrg_bar;  // completes when all 8 x (16 + 2) floats above have landed
 
     const int t       = threadIdx.x;
     const int sub     = t & 15;   // which 8-dim slice of the head
@@ -282,34 +297,46 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
 
     trace_ev(TRACE_ATTN, 0);
     pdl_launch_dependents();
-    cluster_arrive_relaxed();  // "I am running": matched by the wait just before the first remote shared-memory store
+    if (t == 0) {
+        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mrg_bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(uint32_t(ATT_SPLITS * (16 + 2) * 4)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    cluster_arrive();  // "my mbarrier is armed": matched by the wait just before the first remote store (never blocks in practice)
     const __half* kbase = kcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
     const __half* vbase = vcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
-    // two register buffers, always indexed statically (a runtime buffer index would push all 512 bytes per thread into local memory)
-    uint4 kreg0[8], vreg0[8], kreg1[8], vreg1[8];
-    auto load_chunk = [&](uint4 (&kr)[8], uint4 (&vr)[8], int chunk) {
-        const int p0 = chunk * ATT_ROWS;
+    // *pos was advanced by the PREVIOUS step's last kernel, which completed before this step's first kernel released its
+    // dependents (embed_kernel): the position (and below its rotary row) can be fetched ahead of the dependency wait.
+    const int pos = *pos_p;
+    // Chunk geometry: the 8 CTAs x 2 register buffers of a head are 16 chunks in flight; a chunk holds 8 rowlanes x rpl positions,
+    // rpl chosen so that the 16 chunks cover the whole context in ONE pass while it fits (<= 1280 positions) -- every CTA then does
+    // the same work and nothing waits for a second, serialised round of loads.  Longer contexts loop (chunk c -> CTA c mod 8).
+    const int rpl        = min(ATT_RMAX, max(1, (pos + 128) / 128));
+    const int chunk_rows = 8 * rpl;
+    // two register buffers, always indexed statically (a runtime buffer index would push them into local memory)
+    uint4 kreg0[ATT_RMAX], vreg0[ATT_RMAX], kreg1[ATT_RMAX], vreg1[ATT_RMAX];
+    // Rows below the current position were written by earlier STEPS (row `pos` itself is appended by this launch and taken from
+    // shared memory), so these loads need nothing the preceding kernel produces.
+    auto load_chunk = [&](uint4 (&kr)[ATT_RMAX], uint4 (&vr)[ATT_RMAX], int chunk) {
+        const int p0 = chunk * chunk_rows;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < ATT_RMAX; ++i) {
             const int j = p0 + i * 8 + rowlane;
-            kr[i]       = (j < max_ctx) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+            kr[i]       = (i < rpl && j < pos) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < ATT_RMAX; ++i) {
             const int j = p0 + i * 8 + rowlane;
-            vr[i]       = (j < max_ctx) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+            vr[i]       = (i < rpl && j < pos) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
         }
     };
-    // Rows below the current position were written by earlier STEPS and rows above it are masked out later, so these loads
-    // need neither `pos` nor anything the preceding kernel produces.
     load_chunk(kreg0, vreg0, split);
     load_chunk(kreg1, vreg1, split + ATT_SPLITS);
-    // the attention stream is small (the layer's KV rows): use the idle HBM time to pull the head rows of the next GEMV into L2
+    // the attention stream is small (the layer's KV rows): use the idle HBM time to pull the head of the next GEMV's weights into L2
     if (ao.next.w != nullptr && t == ATT_THREADS - 32)
         l2_prefetch_next(ao.next, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
-    // *pos was advanced by the PREVIOUS step's last kernel, which completed before this step's first kernel released its
-    // dependents (embed_kernel): the position and its rotary row can be fetched ahead of the dependency wait as well
-    const int pos = *pos_p;
     float rope_c = 0.f, rope_s = 0.f;
     if (t < ATT_D / 2) {
         rope_c = __half2float(cos_t[int64_t(pos) * (ATT_D / 2) + t]);
@@ -318,7 +345,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     trace_ev(TRACE_ATTN, 1);
     pdl_wait_prior_grids();  // qkv of the current token comes from the preceding GEMV
     trace_ev(TRACE_ATTN, 2);
-    const int new_chunk = pos / ATT_ROWS;
+    const int new_chunk = pos / chunk_rows;
     const bool owns_new = (new_chunk % ATT_SPLITS) == split;
 
     // RoPE of q (every CTA) and of the new k (owner CTA); HF rotate_half convention evaluated in fp16
@@ -326,8 +353,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
         const float c = rope_c, s = rope_s;
         const int a = head * ATT_D + t, b = a + ATT_D / 2;
         const float q0 = __half2float(qkv[a]), q1 = __half2float(qkv[b]);
-        q_s[t]             = __half2float(__hadd(__float2half_rn(q0 * c), __float2half_rn(-q1 * s))) * scale;
-        q_s[t + ATT_D / 2] = __half2float(__hadd(__float2half_rn(q1 * c), __float2half_rn(q0 * s))) * scale;
+        q_s[t]             = __hadd(__float2half_rn(q0 * c), __float2half_rn(-q1 * s));
+        q_s[t + ATT_D / 2] = __hadd(__float2half_rn(q1 * c), __float2half_rn(q0 * s));
         if (owns_new) {
             const float k0 = __half2float(qkv[H + a]), k1 = __half2float(qkv[H + b]);
             const __half r0 = __hadd(__float2half_rn(k0 * c), __float2half_rn(-k1 * s));
@@ -342,21 +369,22 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     }
     __syncthreads();
 
-    float qf[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d)
-        qf[d] = q_s[sub * 8 + d];
+    uint32_t qf[4];
+    {
+        const uint4 qv = *reinterpret_cast<const uint4*>(&q_s[sub * 8]);
+        qf[0] = qv.x; qf[1] = qv.y; qf[2] = qv.z; qf[3] = qv.w;
+    }
     trace_ev(TRACE_ATTN, 3);
 
     // online softmax state of this 16-lane group (identical in all 16 lanes; each lane owns 8 dims of the numerator)
     float m_run = -INFINITY, l_run = 0.f;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    auto process = [&](const uint4 (&kr)[8], const uint4 (&vr)[8], int chunk) {
-        const int p0 = chunk * ATT_ROWS;
-        float sc[8];
+    auto process = [&](const uint4 (&kr)[ATT_RMAX], const uint4 (&vr)[ATT_RMAX], int chunk) {
+        const int p0 = chunk * chunk_rows;
+        float sc[ATT_RMAX];
         float cmax = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < ATT_RMAX; ++i) {
             const int j = p0 + i * 8 + rowlane;
             uint4 kv    = kr[i];
             if (j == pos)
@@ -365,7 +393,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
 #pragma unroll
             for (int o = 8; o >= 1; o >>= 1)
                 d += __shfl_xor_sync(0xffffffffu, d, o);
-            sc[i] = (j <= pos) ? d : -INFINITY;
+            sc[i] = (i < rpl && j <= pos) ? d * scale : -INFINITY;
             cmax  = fmaxf(cmax, sc[i]);
         }
         if (cmax == -INFINITY)
@@ -377,28 +405,29 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
         for (int d = 0; d < 8; ++d)
             acc[d] *= resc;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < ATT_RMAX; ++i) {
             const int j = p0 + i * 8 + rowlane;
             if (sc[i] != -INFINITY) {
-                const float p = __expf(sc[i] - m_new);
-                l_run += p;
+                // the probability is rounded to fp16 once and that SAME value feeds numerator and denominator
+                const __half ph = __float2half_rn(__expf(sc[i] - m_new));
+                l_run += __half2float(ph);
                 uint4 vv = vr[i];
                 if (j == pos)
                     vv = *reinterpret_cast<const uint4*>(&vnew[sub * 8]);
-                axpy8(p, vv, acc);
+                axpy8(uint32_t(__half_as_ushort(ph)), vv, acc);
             }
         }
         m_run = m_new;
     };
 
-    for (int chunk = split; chunk * ATT_ROWS <= pos; chunk += 2 * ATT_SPLITS) {
+    for (int chunk = split; chunk * chunk_rows <= pos; chunk += 2 * ATT_SPLITS) {
         process(kreg0, vreg0, chunk);
-        if ((chunk + 2 * ATT_SPLITS) * ATT_ROWS <= pos)
+        if ((chunk + 2 * ATT_SPLITS) * chunk_rows <= pos)
             load_chunk(kreg0, vreg0, chunk + 2 * ATT_SPLITS);
-        if ((chunk + ATT_SPLITS) * ATT_ROWS > pos)
+        if ((chunk + ATT_SPLITS) * chunk_rows > pos)
             break;
         process(kreg1, vreg1, chunk + ATT_SPLITS);
-        if ((chunk + 3 * ATT_SPLITS) * ATT_ROWS <= pos)
+        if ((chunk + 3 * ATT_SPLITS) * chunk_rows <= pos)
             load_chunk(kreg1, vreg1, chunk + 3 * ATT_SPLITS);
     }
 
@@ -428,16 +457,29 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
         // push: dim t is finished by CTA t / 16 of the cluster; every CTA needs every (max, denominator).  (The wait completes the
         // start-of-kernel phase: every sibling is executing, its shared memory may be written -- it never blocks in practice.)
         cluster_wait();
-        st_dsmem_f32(&mrg_o[split][t & 15], uint32_t(t >> 4), num);
+        st_dsmem_f32_signal(&mrg_o[split][t & 15], &mrg_bar, uint32_t(t >> 4), num);
         if (t < ATT_SPLITS) {
-            st_dsmem_f32(&mrg_ml[split][0], uint32_t(t), mm);
-            st_dsmem_f32(&mrg_ml[split][1], uint32_t(t), den);
+            st_dsmem_f32_signal(&mrg_ml[split][0], &mrg_bar, uint32_t(t), mm);
+            st_dsmem_f32_signal(&mrg_ml[split][1], &mrg_bar, uint32_t(t), den);
         }
     }
-    // ONE cluster barrier: after it every partial this CTA needs sits in its own shared memory, and nobody touches a
-    // sibling's shared memory any more (so CTAs may exit independently)
-    cluster_arrive();
-    cluster_wait();
+    // The 16 finishing threads wait on THIS CTA's mbarrier until all 8 x 18 floats addressed to it have landed; the other threads are
+    // done (nobody reads a sibling's shared memory, and every store's target is kept alive by this very wait).
+    if (t < 16) {
+        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mrg_bar));
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
     trace_ev(TRACE_ATTN, 5);
     if (t < 16) {
         const int d = split * 16 + t;
