@@ -65,6 +65,7 @@ SIGNATURES = {
                                             _c_vp]),
     "eetq_b200_w8a16_gemm_trace_info": (_c_int, [_c_i64, _c_i64, _c_i64, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)]),
     "eetq_b200_set_timeline": (_c_int, [_c_vp, ctypes.c_uint64]),
+    "eetq_b200_decode_attention_occupancy": (_c_int, [_c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)]),
     "eetq_b200_w8a16_gemm_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int,
                                            _c_vp, _c_sz, _c_vp]),
     "eetq_b200_w8a16_gemv_fused": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int,

@@ -195,20 +195,28 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const __half* __restrict_
 
 // ---------------------------------------------------------------------------------------------------------------
 // Decode attention: fused RoPE + KV append + attention for ONE query token, ONE launch per layer, no global scratch.
-//   grid = (local heads, 8), cluster (1, 8, 1), 128 threads, head_dim 128.  The 8 CTAs of a cluster share one head: CTA s
-//   streams the 64-row cache chunks s, s + 8, s + 16, ... (balanced for any position, and static -- so the first two chunks
-//   are requested BEFORE griddepcontrol.wait and before the position is even read, overlapping the tail of the q|k|v GEMV).
-//   Thread (rowlane = t / 16, sub = t % 16) holds 16-byte slices of 8 K rows and 8 V rows of a chunk in registers, two
-//   chunks in flight (512 bytes per thread).  Each 16-lane group runs its own online softmax (no block barriers inside the
-//   stream); the 8 groups are merged through shared memory, the 8 CTAs through DISTRIBUTED shared memory (one cluster barrier
-//   instead of round 1's global scratch + __threadfence + atomic ticket + serial merge).
+//   grid = (local heads, 4), cluster (1, 4, 1), 256 threads, head_dim 128.  The 4 CTAs of a cluster share one head.  The cache is
+//   head-major, so a chunk of positions is ONE contiguous byte range of K and one of V: an elected thread moves them with two bulk
+//   copies (TMA, cp.async.bulk) into shared memory and an mbarrier counts the bytes -- no registers and no load/store-unit slots
+//   are tied up by the stream, the CTA stays small (72 registers) and the next GEMV's CTAs fit beside it.  A head's 8 staging
+//   buffers (4 CTAs x 2) are sized from the position (read ahead of the dependency wait) so that they cover the whole context in
+//   ONE pass up to 1280 positions; longer contexts loop (chunk c -> CTA c mod 4).  The copies are issued BEFORE
+//   griddepcontrol.wait and overlap the tail of the q|k|v GEMV.
+//   Thread (rowlane = t / 16, sub = t % 16) owns 8 dims of the rows of its row lane; each 16-lane group runs its own online
+//   softmax with FHFMA products (no conversions, no block barriers inside the stream); the 16 row lanes are merged through shared
+//   memory, the 4 CTAs through DISTRIBUTED shared memory: partials are pushed with st.async and counted by the receiver's
+//   mbarrier (no cluster barrier, no release fence, no global scratch on the critical path).
 //   The CTA whose chunk holds the newest position rotates k, appends k / v to the cache and uses them from shared memory.
 //   Output: plain fp16 vector, or LL words pushed to every rank (head-sharded attention, see the file header).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ATT_D       = 128;
-constexpr int ATT_THREADS = 128;
-constexpr int ATT_RMAX    = 10;  // cache rows per rowlane in one register buffer (a chunk = 8 rowlanes x rpl <= 80 positions)
-constexpr int ATT_SPLITS  = 8;   // CTAs per head == cluster size
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_LANES   = ATT_THREADS / 16;  // row lanes: 16-thread groups, each walks its own cache rows (a thread holds 8 dims)
+constexpr int ATT_SPLITS  = 4;                 // CTAs per head == cluster size
+constexpr int ATT_OWN     = ATT_D / ATT_SPLITS;  // output dims finished by one CTA of the cluster
+constexpr int ATT_RMAX    = 10;  // cache rows per row lane in one staging buffer (a chunk = ATT_LANES x rpl <= 160 positions)
+constexpr int ATT_BUF_HALF = ATT_LANES * ATT_RMAX * ATT_D * 2;  // bytes of K (or V) in one buffer: 40 KB
+constexpr int ATT_SMEM     = 2 * 2 * ATT_BUF_HALF + 128;        // two buffers of K|V + alignment slack: 160 KB + 128
 
 // acc(fp32) += a(fp16) * b(fp16): one FHFMA on sm_100a (exact product, single fp32 rounding) -- no fp16 -> fp32 conversions
 __device__ __forceinline__ float fhfma(uint32_t a2, uint32_t b2, int hi, float acc)
@@ -283,15 +291,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     __shared__ __align__(16) __half q_s[ATT_D];  // rotated query, fp16 (HF evaluates RoPE in the model dtype)
     __shared__ __align__(16) __half knew[ATT_D];
     __shared__ __align__(16) __half vnew[ATT_D];
-    __shared__ float grp_o[8][ATT_D];   // per 16-lane group partial numerators
-    __shared__ float grp_ml[8][2];      // per group (max, denominator)
-    __shared__ float mrg_o[ATT_SPLITS][16];  // partial numerators of MY 16 output dims, one row pushed by every CTA of the cluster
+    __shared__ float grp_o[ATT_LANES][ATT_D];   // per row-lane partial numerators
+    __shared__ float grp_ml[ATT_LANES][2];      // per row lane (max, denominator)
+    __shared__ float mrg_o[ATT_SPLITS][ATT_OWN];  // partial numerators of MY output dims, one row pushed by every CTA of the cluster
     __shared__ float mrg_ml[ATT_SPLITS][2];  // (max, denominator) of every CTA of the cluster
     __shared__ __align__(8) unsigned long long mrg_bar;  // completes when all 8 x (16 + 2) floats above have landed
+    __shared__ __align__(8) unsigned long long kv_bar[2];  // one per staging buffer: counts the bytes of its K and V bulk copies
 
     const int t       = threadIdx.x;
     const int sub     = t & 15;   // which 8-dim slice of the head
-    const int rowlane = t >> 4;   // 0..7
+    const int rowlane = t >> 4;   // 0 .. ATT_LANES-1
     const int head    = blockIdx.x;
     const int split   = int(cluster_ctarank());  // == blockIdx.y
 
@@ -300,40 +309,51 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     if (t == 0) {
         const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mrg_bar));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(uint32_t(ATT_SPLITS * (16 + 2) * 4)) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(uint32_t(ATT_SPLITS * (ATT_OWN + 2) * 4)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&kv_bar[0]))) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&kv_bar[1]))) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     cluster_arrive();  // "my mbarrier is armed": matched by the wait just before the first remote store (never blocks in practice)
-    const __half* kbase = kcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
-    const __half* vbase = vcache + int64_t(head) * max_ctx * ATT_D + sub * 8;
     // *pos was advanced by the PREVIOUS step's last kernel, which completed before this step's first kernel released its
     // dependents (embed_kernel): the position (and below its rotary row) can be fetched ahead of the dependency wait.
     const int pos = *pos_p;
-    // Chunk geometry: the 8 CTAs x 2 register buffers of a head are 16 chunks in flight; a chunk holds 8 rowlanes x rpl positions,
+    // Chunk geometry: the 8 CTAs x 2 staging buffers of a head are 16 chunks in flight; a chunk holds 8 rowlanes x rpl positions,
     // rpl chosen so that the 16 chunks cover the whole context in ONE pass while it fits (<= 1280 positions) -- every CTA then does
     // the same work and nothing waits for a second, serialised round of loads.  Longer contexts loop (chunk c -> CTA c mod 8).
-    const int rpl        = min(ATT_RMAX, max(1, (pos + 128) / 128));
-    const int chunk_rows = 8 * rpl;
-    // two register buffers, always indexed statically (a runtime buffer index would push them into local memory)
-    uint4 kreg0[ATT_RMAX], vreg0[ATT_RMAX], kreg1[ATT_RMAX], vreg1[ATT_RMAX];
-    // Rows below the current position were written by earlier STEPS (row `pos` itself is appended by this launch and taken from
-    // shared memory), so these loads need nothing the preceding kernel produces.
-    auto load_chunk = [&](uint4 (&kr)[ATT_RMAX], uint4 (&vr)[ATT_RMAX], int chunk) {
-        const int p0 = chunk * chunk_rows;
-#pragma unroll
-        for (int i = 0; i < ATT_RMAX; ++i) {
-            const int j = p0 + i * 8 + rowlane;
-            kr[i]       = (i < rpl && j < pos) ? ldg_stream_128(kbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int i = 0; i < ATT_RMAX; ++i) {
-            const int j = p0 + i * 8 + rowlane;
-            vr[i]       = (i < rpl && j < pos) ? ldg_stream_128(vbase + int64_t(j) * ATT_D) : make_uint4(0u, 0u, 0u, 0u);
+    constexpr int kSlots = 2 * ATT_SPLITS * ATT_LANES;  // row slots per round of the whole cluster (128)
+    const int rpl        = min(ATT_RMAX, max(1, (pos + kSlots) / kSlots));
+    const int chunk_rows = ATT_LANES * rpl;
+    // The rows of a chunk are CONTIGUOUS in the head-major cache: one elected thread moves a chunk's K rows and V rows with two bulk
+    // copies (TMA) into shared memory and an mbarrier counts the bytes.  No registers and no load/store-unit slots are tied up by the
+    // stream, so the CTA stays small (the next GEMV's CTAs fit beside it and start THEIR weight stream during the attention).
+    // Rows below the position were written by earlier STEPS (row `pos` itself is appended by this launch and taken from shared
+    // memory), so the copies need nothing the preceding kernel produces.
+    extern __shared__ uint8_t att_dyn[];
+    const uint32_t kv_base = (static_cast<uint32_t>(__cvta_generic_to_shared(att_dyn)) + 127u) & ~127u;
+    auto issue_chunk = [&](int buf, int chunk) {  // thread 0 only
+        const int p0     = chunk * chunk_rows;
+        const int n      = min(chunk_rows, pos - p0);  // rows strictly below the position
+        const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(&kv_bar[buf]));
+        const uint32_t bytes = n > 0 ? uint32_t(n) * ATT_D * 2 : 0u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(2u * bytes) : "memory");
+        if (n > 0) {
+            const __half* ks = kcache + (int64_t(head) * max_ctx + p0) * ATT_D;
+            const __half* vs = vcache + (int64_t(head) * max_ctx + p0) * ATT_D;
+            const uint32_t kd = kv_base + uint32_t(buf) * 2u * ATT_BUF_HALF;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(kd), "l"(ks),
+                         "r"(bytes), "r"(b)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(kd + ATT_BUF_HALF),
+                         "l"(vs), "r"(bytes), "r"(b)
+                         : "memory");
         }
     };
-    load_chunk(kreg0, vreg0, split);
-    load_chunk(kreg1, vreg1, split + ATT_SPLITS);
+    if (t == 0) {
+        issue_chunk(0, split);
+        issue_chunk(1, split + ATT_SPLITS);
+    }
     // the attention stream is small (the layer's KV rows): use the idle HBM time to pull the head of the next GEMV's weights into L2
     if (ao.next.w != nullptr && t == ATT_THREADS - 32)
         l2_prefetch_next(ao.next, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
@@ -379,17 +399,42 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
     // online softmax state of this 16-lane group (identical in all 16 lanes; each lane owns 8 dims of the numerator)
     float m_run = -INFINITY, l_run = 0.f;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    auto process = [&](const uint4 (&kr)[ATT_RMAX], const uint4 (&vr)[ATT_RMAX], int chunk) {
-        const int p0 = chunk * chunk_rows;
+    auto wait_buf = [&](int buf, uint32_t parity) {
+        const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(&kv_bar[buf]));
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(done)
+                : "r"(b), "r"(parity)
+                : "memory");
+        }
+    };
+    auto lds_row = [&](uint32_t base, int row) -> uint4 {  // this thread's 8 dims of a staged row (a warp reads 2 whole rows: no conflicts)
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + uint32_t(row) * (ATT_D * 2) + uint32_t(sub) * 16u));
+        return v;
+    };
+    auto process = [&](int buf, int chunk) {
+        const int p0       = chunk * chunk_rows;
+        const uint32_t kb  = kv_base + uint32_t(buf) * 2u * ATT_BUF_HALF;
+        const uint32_t vb  = kb + ATT_BUF_HALF;
         float sc[ATT_RMAX];
         float cmax = -INFINITY;
 #pragma unroll
         for (int i = 0; i < ATT_RMAX; ++i) {
-            const int j = p0 + i * 8 + rowlane;
-            uint4 kv    = kr[i];
-            if (j == pos)
-                kv = *reinterpret_cast<const uint4*>(&knew[sub * 8]);  // the row appended by this very launch
-            float d = dot8(kv, qf);
+            const int r = i * ATT_LANES + rowlane;
+            const int j = p0 + r;
+            float d     = 0.f;
+            if (i < rpl && j <= pos) {  // uniform inside the 16-lane group
+                const uint4 kv = (j == pos) ? *reinterpret_cast<const uint4*>(&knew[sub * 8])  // the row appended by this very launch
+                                            : lds_row(kb, r);
+                d = dot8(kv, qf);
+            }
 #pragma unroll
             for (int o = 8; o >= 1; o >>= 1)
                 d += __shfl_xor_sync(0xffffffffu, d, o);
@@ -406,33 +451,37 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
             acc[d] *= resc;
 #pragma unroll
         for (int i = 0; i < ATT_RMAX; ++i) {
-            const int j = p0 + i * 8 + rowlane;
+            const int r = i * ATT_LANES + rowlane;
+            const int j = p0 + r;
             if (sc[i] != -INFINITY) {
                 // the probability is rounded to fp16 once and that SAME value feeds numerator and denominator
                 const __half ph = __float2half_rn(__expf(sc[i] - m_new));
                 l_run += __half2float(ph);
-                uint4 vv = vr[i];
-                if (j == pos)
-                    vv = *reinterpret_cast<const uint4*>(&vnew[sub * 8]);
+                const uint4 vv = (j == pos) ? *reinterpret_cast<const uint4*>(&vnew[sub * 8]) : lds_row(vb, r);
                 axpy8(uint32_t(__half_as_ushort(ph)), vv, acc);
             }
         }
         m_run = m_new;
     };
 
-    for (int chunk = split; chunk * chunk_rows <= pos; chunk += 2 * ATT_SPLITS) {
-        process(kreg0, vreg0, chunk);
-        if ((chunk + 2 * ATT_SPLITS) * chunk_rows <= pos)
-            load_chunk(kreg0, vreg0, chunk + 2 * ATT_SPLITS);
-        if ((chunk + ATT_SPLITS) * chunk_rows > pos)
-            break;
-        process(kreg1, vreg1, chunk + ATT_SPLITS);
-        if ((chunk + 3 * ATT_SPLITS) * chunk_rows <= pos)
-            load_chunk(kreg1, vreg1, chunk + 3 * ATT_SPLITS);
+    {
+        int it = 0;
+        for (int chunk = split; chunk * chunk_rows <= pos; chunk += ATT_SPLITS, ++it) {
+            const int buf = it & 1;
+            wait_buf(buf, uint32_t(it >> 1) & 1u);
+            process(buf, chunk);
+            const int nxt = chunk + 2 * ATT_SPLITS;
+            if (nxt * chunk_rows <= pos) {  // contexts beyond one pass: refill this buffer once every thread has consumed it
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (t == 0)
+                    issue_chunk(buf, nxt);
+            }
+        }
     }
 
     trace_ev(TRACE_ATTN, 4);
-    // merge the 8 groups of this CTA
+    // merge the row lanes of this CTA
 #pragma unroll
     for (int d = 0; d < 8; ++d)
         grp_o[rowlane][sub * 8 + d] = acc[d];
@@ -441,31 +490,34 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
         grp_ml[rowlane][1] = l_run;
     }
     __syncthreads();
-    {
+    if (t < ATT_D) {
         float mm = -INFINITY;
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < ATT_LANES; ++r)
             mm = fmaxf(mm, grp_ml[r][0]);
         float num = 0.f, den = 0.f;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < ATT_LANES; ++r) {
             const float mr = grp_ml[r][0];
             const float w  = (mr == -INFINITY) ? 0.f : __expf(mr - mm);
             num = fmaf(w, grp_o[r][t], num);
             den = fmaf(w, grp_ml[r][1], den);
         }
-        // push: dim t is finished by CTA t / 16 of the cluster; every CTA needs every (max, denominator).  (The wait completes the
-        // start-of-kernel phase: every sibling is executing, its shared memory may be written -- it never blocks in practice.)
+        // push: dim t is finished by CTA t / ATT_OWN of the cluster; every CTA needs every (max, denominator).  (The wait completes
+        // the start-of-kernel phase: every sibling has armed its mbarrier -- it never blocks in practice.)
         cluster_wait();
-        st_dsmem_f32_signal(&mrg_o[split][t & 15], &mrg_bar, uint32_t(t >> 4), num);
+        st_dsmem_f32_signal(&mrg_o[split][t % ATT_OWN], &mrg_bar, uint32_t(t / ATT_OWN), num);
         if (t < ATT_SPLITS) {
             st_dsmem_f32_signal(&mrg_ml[split][0], &mrg_bar, uint32_t(t), mm);
             st_dsmem_f32_signal(&mrg_ml[split][1], &mrg_bar, uint32_t(t), den);
         }
     }
-    // The 16 finishing threads wait on THIS CTA's mbarrier until all 8 x 18 floats addressed to it have landed; the other threads are
-    // done (nobody reads a sibling's shared memory, and every store's target is kept alive by this very wait).
-    if (t < 16) {
+    else {
+        cluster_wait();  // every thread that arrived at the start-of-kernel phase also completes it
+    }
+    // The finishing threads wait on THIS CTA's mbarrier until all ATT_SPLITS x (ATT_OWN + 2) floats addressed to it have landed; the
+    // other threads are done (nobody reads a sibling's shared memory, and every store's target is kept alive by this very wait).
+    if (t < ATT_OWN) {
         const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mrg_bar));
         uint32_t done = 0;
         while (!done) {
@@ -481,8 +533,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
         }
     }
     trace_ev(TRACE_ATTN, 5);
-    if (t < 16) {
-        const int d = split * 16 + t;
+    if (t < ATT_OWN) {
+        const int d = split * ATT_OWN + t;
         float mm = -INFINITY;
 #pragma unroll
         for (int r = 0; r < ATT_SPLITS; ++r)
@@ -502,7 +554,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const __half* 
         else {
             // LL: lanes pair up (even lane carries dims d, d + 1) and push one 8-byte word per rank
             const uint32_t mine  = uint32_t(__half_as_ushort(o));
-            const uint32_t other = __shfl_down_sync(0x0000ffffu, mine, 1);
+            const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 1);
             if ((t & 1) == 0)
                 ll_push_word(ao.push, (head * ATT_D + d) >> 1, mine | (other << 16));
         }
@@ -908,11 +960,33 @@ int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* s
     const int heads = int(H_local / D);
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
-    launch_cfg(cfg, attr, dim3(unsigned(heads), ATT_SPLITS), dim3(ATT_THREADS), 0, pdl != 0, static_cast<cudaStream_t>(stream), ATT_SPLITS);
+    {
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            EB_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+            attr_set[dev] = true;
+        }
+    }
+    launch_cfg(cfg, attr, dim3(unsigned(heads), ATT_SPLITS), dim3(ATT_THREADS), ATT_SMEM, pdl != 0, static_cast<cudaStream_t>(stream), ATT_SPLITS);
     EB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel, static_cast<const __half*>(qkv), static_cast<const __half*>(cos_t),
                                      static_cast<const __half*>(sin_t), static_cast<const int*>(pos_i32), static_cast<__half*>(kcache),
                                      static_cast<__half*>(vcache), int(H_local), int(max_ctx), 1.0f / sqrtf(float(D)), ao));
     count_launch();
+    return EETQ_B200_OK;
+}
+
+// Development aid: how many CTAs / 8-CTA clusters of the decode attention kernel fit on the current device at once.
+int eetq_b200_decode_attention_occupancy(int heads, int* ctas_per_sm, int* max_clusters)
+{
+    EB_CHECK_ARG(ctas_per_sm && max_clusters && heads > 0, "decode_attention_occupancy: bad argument");
+    EB_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    EB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, attn_decode_kernel, ATT_THREADS, ATT_SMEM));
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    launch_cfg(cfg, attr, dim3(unsigned(heads), ATT_SPLITS), dim3(ATT_THREADS), ATT_SMEM, false, nullptr, ATT_SPLITS);
+    EB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, attn_decode_kernel, &cfg));
     return EETQ_B200_OK;
 }
 

@@ -138,6 +138,9 @@ int eetq_b200_w8a16_gemm_trace(const void* x, int64_t ldx, const int8_t* w_b200,
                                void* stream);
 int eetq_b200_w8a16_gemm_trace_info(int64_t M, int64_t N, int64_t K, int* grid, int* slots);
 
+/* Development aid: resident CTAs per SM and resident 8-CTA clusters of the decode attention kernel on the current device. */
+int eetq_b200_decode_attention_occupancy(int heads, int* ctas_per_sm, int* max_clusters);
+
 /* Development aid: point the decode kernels' in-situ timeline recorder at a device buffer of (2 + 2 * capacity) 64-bit words
  * ([0] = record count; zero the buffer first; records are {tag << 56 | block << 16 | event, %globaltimer ns}).  Only a library
  * built with EETQ_B200_BUILD_TRACE=1 records; the product build ignores the call.  Returns 1 if recording is compiled in, else 0. */
@@ -228,8 +231,8 @@ int eetq_b200_prefill_rope_kv(void* qkv, int64_t ld, const void* cos_t, const vo
 /* Prefill glue: act[t][i] = fp16(silu(gate)) * up; interleaved = 0: rows are gate[I] | up[I], 1: (g0, u0, g1, u1, ...) */
 int eetq_b200_silu_mul(const void* gu, int64_t ldg, void* act, int64_t lda, int64_t T, int64_t I, int interleaved, void* stream);
 /* Fused RoPE (rotate_half convention) + KV-cache append + attention for ONE token at position *pos, head_dim 128, ONE
- * launch: grid (local heads, 8) in clusters of 8 CTAs per head; the KV stream is register-fed and starts before the
- * dependency wait; the 8 partial results of a head are merged through distributed shared memory.
+ * launch: grid (local heads, 4) in clusters of 4 CTAs per head; the KV stream is moved by bulk copies (TMA) into shared memory
+ * and starts before the dependency wait; the 4 partial results of a head are merged through distributed shared memory.
  *   qkv [3 * H_local] = q | k | v raw projections of this rank's heads; cos/sin [max_pos][D/2]; kcache/vcache
  *   [H_local/D][max_ctx][D] head-major (row *pos of every head is written); out [H_local] plain fp16, or NULL and `push`
  *   describes the LL exchange of the full attention vector (elem_off = first element of this rank's heads).
