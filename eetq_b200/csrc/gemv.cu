@@ -305,7 +305,8 @@ struct GemvFuse {
     LLTag res_ll;   // tag_base != nullptr: residual points at LL words of the full output vector; element offset res_off
     int res_off;
     LLPush push;    // world > 0: outputs are pushed as LL words to every rank instead of being stored to y
-    NextHint next;  // w != nullptr: ask L2 for the next GEMV's per-CTA head rows when this CTA leaves its main loop
+    NextHint next;  // w != nullptr: ask L2 for the head of the next GEMV's weights
+    int nowait;     // != 0: every input is an LL buffer (data carries its own tag): do not wait for the previous grid to complete
 };
 
 template <typename T, int M, int KITERS, int R, bool XREG>
@@ -405,7 +406,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
             }
         }
         trace_ev(TRACE_GEMV, 1);
-        pdl_wait_prior_grids();
+        // Plain inputs become valid when the previous grid has COMPLETED (griddepcontrol.wait returns ~1.4 us after its last CTA);
+        // LL inputs carry their own tags, polled word by word below, so the chain of decode kernels need not drain between stages.
+        if (fuse.nowait == 0)
+            pdl_wait_prior_grids();
         trace_ev(TRACE_GEMV, 2);
         // the residual of this thread's output element travels together with the activations
         if constexpr (M == 1) {
@@ -748,6 +752,13 @@ GemvFuse<T> make_fuse(const GemvExtras& ex)
     f.res_ll      = ex.res_ll;
     f.res_off     = ex.res_off;
     f.push        = ex.push;
+    // measured on one GPU with local LL buffers: skipping the wait is slower (509 vs 537 tok/s, the early pollers compete with the
+    // producer's weight stream), so it stays opt-in
+    static const bool ll_nowait = [] {
+        const char* e = getenv("EETQ_B200_LL_NOWAIT");
+        return e != nullptr && e[0] == '1';
+    }();
+    f.nowait = (ll_nowait && ex.x_ll.tag_base != nullptr && (ex.residual == nullptr || ex.res_ll.tag_base != nullptr)) ? 1 : 0;
     static const bool l2_next = [] {
         const char* e = getenv("EETQ_B200_L2_NEXT");
         return !(e != nullptr && e[0] == '0');

@@ -215,7 +215,15 @@ class W8A16LlamaDecoder:
                  group=None, exchange: Optional[str] = None):
         self.shape, self.max_ctx, self.pdl = shape, max_ctx, bool(pdl)
         self.rank, self.world, self.group = rank, world_size, group
-        self.exchange = (exchange or os.environ.get("EETQ_B200_EXCHANGE", "ll")) if world_size > 1 else "none"
+        if world_size > 1:
+            self.exchange = exchange or os.environ.get("EETQ_B200_EXCHANGE", "ll")
+        else:
+            # one GPU: plain vectors + griddepcontrol.wait ("none").  The tagged-word buffers of the multi-GPU path also work here
+            # ("ll", no kernel waits for its predecessor to drain) but measured slower: 509 vs 633 tok/s -- 296 CTAs polling for the
+            # activation words slow the producer's weight stream down more than the skipped drain saves.
+            self.exchange = exchange or os.environ.get("EETQ_B200_LOCAL_EXCHANGE", "none")
+            if self.exchange == "nccl":
+                self.exchange = "none"
         assert self.exchange in ("none", "ll", "nccl")
         plan = self.plan = shard_plan(shape, rank, world_size)
         m = model.model
@@ -275,8 +283,9 @@ class W8A16LlamaDecoder:
     # ------------------------------------------------------------------------------------------------- LL exchange buffers
     def _setup_ll(self, H, I, dev):
         """LL buffers (8-byte words {2 x fp16, tag}) in ONE symmetric-memory arena mapped into every rank."""
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
+        if self.world > 1:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
 
         def rnd(n):
             return (n + 255) // 256 * 256
@@ -286,6 +295,10 @@ class W8A16LlamaDecoder:
         for name, nb in sizes:
             offs[name] = total
             total += rnd(nb)
+        if self.world == 1:
+            arena = torch.zeros(total, dtype=torch.uint8, device=dev)  # tag 0 is never a valid tag
+            self._ll = dict(arena=arena, hdl=None, bases=[arena.data_ptr()], offs=offs)
+            return
         arena = symm_mem.empty(total, dtype=torch.uint8, device=dev)
         arena.zero_()  # tag 0 is never a valid tag
         group = self.group if self.group is not None else dist.group.WORLD
@@ -407,10 +420,11 @@ class W8A16LlamaDecoder:
         v0 = plan["vocab"][0]
         if ll:
             xt = self._tag(plan["x_out"](len(self.layers) - 1))
-            cand = self._push("cand", 0, plan["cand"])
+            cand = self._push("cand", 0, plan["cand"]) if self.world > 1 else None
             rc = L.eetq_b200_lm_head_argmax(ctypes.c_void_p(self._ll_local("x")), ctypes.byref(xt), _vp(self.norm_w), float(s.eps),
                                             _vp(self.lm_head_w), self.Vl, H, v0, _vp(self.logits), _vp(self.lm_scratch), _vp(self.token),
-                                            _vp(self.pos), _vp(self.step_ctr), ctypes.byref(cand), self.rank, pdl, st())
+                                            _vp(self.pos), _vp(self.step_ctr), ctypes.byref(cand) if cand is not None else None,
+                                            self.rank, pdl, st())
             _cabi.check(rc, "lm_head_argmax")
         else:
             rc = L.eetq_b200_lm_head_argmax(_vp(self.x), None, _vp(self.norm_w), float(s.eps), _vp(self.lm_head_w), self.Vl, H, v0,
@@ -518,7 +532,7 @@ class W8A16LlamaDecoder:
         # first new token: final norm + lm_head + arg-max on the last row (the kernel advances pos and the step counter)
         last = x[-1].contiguous()
         self.pos.fill_(T - 1)
-        cand = self._push("cand", 0, plan["cand"]) if self._ll is not None else None
+        cand = self._push("cand", 0, plan["cand"]) if (self._ll is not None and self.world > 1) else None
         rc = L.eetq_b200_lm_head_argmax(_vp(last), None, _vp(self.norm_w), float(s.eps), _vp(self.lm_head_w), self.Vl, H, plan["vocab"][0],
                                         _vp(self.logits), _vp(self.lm_scratch), _vp(self.token), _vp(self.pos), _vp(self.step_ctr),
                                         ctypes.byref(cand) if cand is not None else None, self.rank, 0, st)
