@@ -421,14 +421,42 @@ __device__ __forceinline__ void epilogue_columns(const TcParams& p, const Segmen
                     }
             }
         }
+        // The 4 epilogue warps are ONE warp per scheduler, i.e. latency-bound on every dependent instruction: keep the per-element
+        // work to convert + store + pointer bump (the straightforward indexed form cost ~25 instructions per element and made the
+        // epilogue of a 256-token tile as long as its whole main loop).
+        const int t0   = sg.t_tile * BT + c0;
+        const int tcnt = n_ok ? min(16, p.M - t0) : 0;  // valid token rows of this chunk (<= 0: nothing to store)
+        T* yp          = y + int64_t(t0) * p.ldy + n;
+        if (p.residual == nullptr) {
+            if (tcnt == 16) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int t = sg.t_tile * BT + c0 + j;
-            if (n_ok && t < p.M) {
-                T o = from_float<T>(v[j] * scale_f + bias_f);
-                if (p.residual != nullptr)
-                    o = from_float<T>(to_float(o) + to_float(static_cast<const T*>(p.residual)[int64_t(t) * p.ldr + n]));
-                y[int64_t(t) * p.ldy + n] = o;
+                for (int j = 0; j < 16; ++j) {
+                    *yp = from_float<T>(v[j] * scale_f + bias_f);
+                    yp += p.ldy;
+                }
+            }
+            else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j < tcnt)
+                        *yp = from_float<T>(v[j] * scale_f + bias_f);
+                    yp += p.ldy;
+                }
+            }
+        }
+        else {
+            const T* rp = static_cast<const T*>(p.residual) + int64_t(t0) * p.ldr + n;
+            T rv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {  // all residual loads first (independent), then the adds and stores
+                rv[j] = (j < tcnt) ? *rp : from_float<T>(0.f);
+                rp += p.ldr;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (j < tcnt)
+                    *yp = from_float<T>(to_float(from_float<T>(v[j] * scale_f + bias_f)) + to_float(rv[j]));
+                yp += p.ldy;
             }
         }
     }
@@ -525,17 +553,9 @@ __global__ void __launch_bounds__(tc_threads(DQW), 1)
 
     // The last segment of a CTA's range may be an OWNED tile whose remaining k range was computed by the following CTAs:
     // its epilogue (own accumulator + their partials) is done by the epilogue AND dequant warps together at the very end.
-    bool last_is_fixup = false;
-    {
-        // walk to the last segment (at most a handful of iterations)
-        int u = u0;
-        Segment sg{};
-        while (u < u1) {
-            sg = segment_at(p, u, u1);
-            u += sg.s1 - sg.s0;
-        }
-        last_is_fixup = (u1 > u0) && sg.s0 == 0 && sg.s1 < p.spt;
-    }
+    // (Closed form -- the segment walk this replaces sat in front of the role dispatch and delayed the first TMA by ~0.6 us.)
+    const int last_tile0    = ((u1 - 1) / p.spt) * p.spt;  // first unit of the tile that holds this CTA's last unit
+    const bool last_is_fixup = (u1 > u0) && last_tile0 >= u0 && u1 < last_tile0 + p.spt;
 
     if (warp == W_PRODUCER_WARP) {
         // ============================================================== weight TMA producer (whole warp loops, one lane issues)
@@ -923,6 +943,15 @@ TcConfig choose_config(int64_t M, int64_t N, int64_t K, bool have_workspace)
     c.t_tiles       = int((M + bt - 1) / bt);
     const int tiles = c.n_tiles * c.t_tiles;
     const int64_t U = int64_t(tiles) * c.spt;
+    // Whole tiles per CTA (no partial exchange) win when one wave of tiles already fills most of the machine: the partial dump +
+    // owner fix-up of the stream-K schedule costs a fixed 2-4 us.  Measured cut-offs (kbench, profiles/r02_kbench_tc.jsonl).
+    {
+        const int waves   = (tiles + sms - 1) / sms;
+        const double fill = double(tiles) / (double(waves) * sms);
+        const bool aligned_wins = bt <= 64 ? fill >= 0.55 : (fill >= 0.85 && c.spt <= 24);
+        if (aligned_wins)
+            have_workspace = false;
+    }
     if (have_workspace) {
         // at least two stages per CTA when there is that much work, and never more than ~64 CTAs sharing one tile (the
         // owner polls one flag per contributor with its 128 epilogue threads)
