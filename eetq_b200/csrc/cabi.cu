@@ -220,6 +220,12 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
         EB_CHECK_ARG(M <= EETQ_B200_GEMV_MAX_M, "w8a16_gemm: FORCE_GEMV needs M <= %d", EETQ_B200_GEMV_MAX_M);
         use_gemv = true;
     }
+    else if (M >= 3 && K * N >= (int64_t(32) << 20)) {
+        // measured (profiles/r02_kbench_*.json): on the large Llama shapes the tcgen05 kernel with a 16-token tile streams the
+        // weights faster than the mma.sync kernel and than the reference GEMV for 3 and 4 rows (4096x11008: 14.1 vs 16.5 / 15.9 us;
+        // 11008x4096: 15.7 vs 19.9 / 15.1 us); the small 4096x4096 shape stays on the streaming kernels (8.5 vs 10.6 us)
+        use_gemv = false;
+    }
     if ((flags & EETQ_B200_FLAG_FORCE_TC) || trace != nullptr)
         use_gemv = false;
 

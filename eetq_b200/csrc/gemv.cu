@@ -709,7 +709,7 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     }
     EB_GEMV_CASE(1, 8, 4)
     EB_GEMV_CASE(2, 4, 2)
-    EB_GEMV_CASE(3, 2, 1)
+    EB_GEMV_CASE(3, (M == 1 ? 2 : 4), 1)  // M = 2 runs one CTA per SM there: four rows per group keep enough bytes in flight
     EB_GEMV_CASE(4, 2, 1)
 #undef EB_GEMV_CASE
     // general path: activations re-read through L1 (no fused prologue / LL input there)

@@ -183,7 +183,7 @@ def _check_gemm_args(x: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor,
 def _gemm_into(x2: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor], out2: torch.Tensor,
                M: int, N: int, K: int, flags: int = _cabi.FLAG_DEFAULT, residual: Optional[torch.Tensor] = None) -> None:
     L = _cabi.lib()
-    ws_bytes = int(L.eetq_b200_workspace_bytes(M, N, K)) if M > 4 else 0
+    ws_bytes = int(L.eetq_b200_workspace_bytes(M, N, K)) if M > 2 else 0  # 3 and 4 rows go to the tcgen05 kernel on the large shapes
     ws = _workspace(x2.device, ws_bytes)
     # a single row has no meaningful row stride (torch allows anything there): pass the contiguous value
     ldx = x2.stride(0) if M > 1 else K

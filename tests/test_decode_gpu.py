@@ -206,6 +206,19 @@ def test_pdl_and_plain_launch_agree(cuda):
     assert outs[0] == outs[1]
 
 
+def test_tagged_word_exchange_on_one_gpu_matches_plain_buffers(cuda):
+    """The multi-GPU activation exchange ("LL" words: {2 x fp16, tag} pushed by the producing kernel's epilogue, polled by the
+    consumer's prologue) also runs with a single rank.  Same kernels, same arithmetic: the tokens must equal the plain-buffer path."""
+    shape = LlamaShape(hidden=1024, inter=2816, layers=3, heads=8, vocab=2048, name="ll-1gpu")
+    model = LlamaSkeleton(shape, device=cuda, seed=21, std=0.05)
+    eetq_b200.eet_quantize(model)
+    prompt = torch.randint(0, shape.vocab, (70,), device=cuda)
+    plain = W8A16LlamaDecoder.from_model(model, max_ctx=128, exchange="none")
+    tagged = W8A16LlamaDecoder.from_model(model, max_ctx=128, exchange="ll")
+    assert plain.exchange == "none" and tagged.exchange == "ll"
+    assert plain.generate(prompt, 24) == tagged.generate(prompt, 24)
+
+
 def test_decode_on_7b_shaped_layers_long_context(cuda):
     """Two Llama-2-7B-shaped layers decoded at a context where every attention CTA walks several chunks; tokens must be
     reproducible and equal between a graph replay and a fresh decoder."""
