@@ -14,15 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeetq_b200.so")
 SOURCES = ["cabi.cu", "quantize.cu", "gemv.cu", "gemv_mma.cu", "gemm_tc.cu", "decode_ops.cu"]
-# development only: EETQ_B200_BUILD_V1=1 also compiles the round-1 tcgen05 kernel as an A/B baseline (EETQ_B200_TC_IMPL=v1)
-if os.environ.get("EETQ_B200_BUILD_V1") == "1":
-    SOURCES.append("gemm_tc_v1.cu")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
-if os.environ.get("EETQ_B200_BUILD_V1") == "1":
-    NVCC_FLAGS.append("-DEETQ_B200_WITH_V1")
 # development only: EETQ_B200_BUILD_TRACE=1 compiles the in-situ timeline recorder into the decode kernels (tools/timeline.py)
 if os.environ.get("EETQ_B200_BUILD_TRACE") == "1":
     NVCC_FLAGS.append("-DEETQ_B200_TRACE")

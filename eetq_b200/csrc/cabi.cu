@@ -168,28 +168,10 @@ size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K)
 {
     if (M <= 0 || N <= 0 || K <= 0)
         return 0;
-    size_t need = gemm_tc_workspace_bytes(M, N, K);
-#ifdef EETQ_B200_WITH_V1
-    const size_t v1 = gemm_tc_v1_workspace_bytes(M, N, K);
-    if (v1 > need) need = v1;
-#endif
-    return need;
+    return gemm_tc_workspace_bytes(M, N, K);
 }
 
 namespace {
-bool use_v1()
-{
-#ifdef EETQ_B200_WITH_V1
-    static const bool v = [] {
-        const char* e = getenv("EETQ_B200_TC_IMPL");
-        return e != nullptr && e[0] == 'v' && e[1] == '1';
-    }();
-    return v;
-#else
-    return false;
-#endif
-}
-
 // EETQ_B200_GEMV_MMA=0 sends M = 2..8 back to the SIMT kernel (A/B measurements)
 bool gemv_mma_on()
 {
@@ -238,10 +220,6 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
         ex.ldr      = ldr;
         return launch_gemv(x, ldx, w_b200, scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl, s);
     }
-#ifdef EETQ_B200_WITH_V1
-    if (use_v1() && residual == nullptr && trace == nullptr)
-        return launch_gemm_tc_v1(x, ldx, w_b200, scales, bias, y, ldy, M, N, K, dtype, workspace, workspace_bytes, pdl, s);
-#endif
     return launch_gemm_tc(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, M, N, K, dtype, workspace, workspace_bytes, pdl, trace, s);
 }
 }  // namespace

@@ -149,13 +149,6 @@ int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scal
                    size_t workspace_bytes, bool pdl, unsigned long long* trace, cudaStream_t stream);
 int gemm_tc_trace_slots();
 int gemm_tc_grid_for(int64_t M, int64_t N, int64_t K);
-#ifdef EETQ_B200_WITH_V1
-// round-1 kernel, A/B baseline only (EETQ_B200_TC_IMPL=v1)
-size_t gemm_tc_v1_workspace_bytes(int64_t M, int64_t N, int64_t K);
-int launch_gemm_tc_v1(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y,
-                      int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes,
-                      bool pdl, cudaStream_t stream);
-#endif
 
 // ---- small device helpers ----------------------------------------------------------------------------
 template <typename T>

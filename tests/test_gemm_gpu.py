@@ -190,6 +190,30 @@ def test_repeatability_and_split_k_workspace_reuse(cuda, oracle):
     assert all(torch.equal(ys[0], y) for y in ys[1:])
 
 
+@pytest.mark.parametrize("M", [1, 3, 48])
+def test_host_buffer_entry_point(cuda, oracle, M):
+    """eetq_b200_w8a16_gemm_host: pinned host activations in, pinned host outputs back (H2D copy, kernel, D2H copy on one stream)."""
+    K, N = 1024, 512
+    q, s, wq, sd = make(oracle, cuda, K, N, seed=17)
+    L = _cabi.lib()
+    x_h = oracle.synth_act(M, K, seed=2).pin_memory()
+    y_h = torch.zeros(M, N, dtype=torch.float16).pin_memory()
+    x_d = torch.empty(M, K, dtype=torch.float16, device=cuda)
+    y_d = torch.empty(M, N, dtype=torch.float16, device=cuda)
+    nbytes = int(L.eetq_b200_workspace_bytes(M, N, K))
+    ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=cuda)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = torch.cuda.current_stream()
+    rc = L.eetq_b200_w8a16_gemm_host(vp(x_h), vp(x_d), vp(wq), vp(sd), None, vp(y_d), vp(y_h), M, N, K, _cabi.F16, vp(ws), nbytes,
+                                     ctypes.c_void_p(st.cuda_stream))
+    _cabi.check(rc, "eetq_b200_w8a16_gemm_host")
+    st.synchronize()
+    assert oracle.norm_rel_err(y_h, ref_out(oracle, x_h, q, s)) <= TOL[torch.float16]
+    assert torch.equal(y_h, y_d.cpu())
+    # null host pointers are rejected without touching the device
+    assert L.eetq_b200_w8a16_gemm_host(None, vp(x_d), vp(wq), vp(sd), None, vp(y_d), vp(y_h), M, N, K, _cabi.F16, None, 0, None) == -1
+
+
 def test_cuda_graph_capture(cuda, oracle):
     K, N = 4096, 4096
     q, s, wq, sd = make(oracle, cuda, K, N)
