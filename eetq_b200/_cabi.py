@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("EETQ_B200_LIB") or os.path.join(_HERE, "libeetq_b200.
 F16, BF16, F32 = 0, 1, 2
 FLAG_DEFAULT, FLAG_FORCE_GEMV, FLAG_FORCE_TC, FLAG_PDL = 0, 1, 2, 4
 GEMV_MAX_M = 8
+GEMV4_MAX_M = 4
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -56,6 +57,14 @@ SIGNATURES = {
     "eetq_b200_from_ref_layout": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "eetq_b200_to_ref_layout": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "eetq_b200_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i64]),
+    "eetq_b200_quantize4": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "eetq_b200_pack4": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "eetq_b200_unpack4": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "eetq_b200_from_ref_layout4": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "eetq_b200_to_ref_layout4": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "eetq_b200_w4a16_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i64]),
+    "eetq_b200_w4a16_gemm": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_sz,
+                                      _c_int, _c_vp]),
     "eetq_b200_w8a16_gemm": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_sz, _c_vp]),
     "eetq_b200_w8a16_gemm_ex": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int,
                                          _c_vp, _c_sz, _c_int, _c_vp]),

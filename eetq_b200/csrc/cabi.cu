@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "int4_layout.cuh"
 
 namespace eetq_b200 {
 
@@ -327,6 +328,93 @@ int eetq_b200_w8a16_gemm(const void* x, const int8_t* w_b200, const void* scales
 {
     return eetq_b200_w8a16_gemm_ex(x, K, w_b200, scales, bias, y, N, M, N, K, dtype, workspace, workspace_bytes,
                                    EETQ_B200_FLAG_DEFAULT, stream);
+}
+
+// ---- packed int4 ------------------------------------------------------------------------------------------------------------
+int eetq_b200_quantize4(const void* w_kn, int w_dtype, int64_t K, int64_t N, uint8_t* q4_b200, void* scales, float* s32,
+                        uint8_t* q4_kn, void* stream)
+{
+    EB_CHECK_ARG(w_kn && q4_b200 && scales && s32, "quantize4: null pointer argument");
+    EB_CHECK_ARG(aligned16(w_kn) && aligned16(q4_b200) && (q4_kn == nullptr || aligned16(q4_kn)),
+                 "quantize4: pointers must be 16-byte aligned");
+    if (int rc = check_kn("quantize4", K, N))
+        return rc;
+    if (int rc = check_arch())
+        return rc;
+    return launch_quantize4(w_kn, w_dtype, K, N, q4_b200, scales, s32, q4_kn, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+int nibble_layout_entry(const char* who, int mode, const uint8_t* src, int64_t K, int64_t N, uint8_t* dst, void* stream)
+{
+    EB_CHECK_ARG(src && dst, "%s: null pointer argument", who);
+    EB_CHECK_ARG(src != dst, "%s: in-place conversion is not supported", who);
+    EB_CHECK_ARG(aligned16(src) && aligned16(dst), "%s: pointers must be 16-byte aligned", who);
+    if (int rc = check_kn(who, K, N))
+        return rc;
+    if (int rc = check_arch())
+        return rc;
+    return launch_nibble_layout(mode, src, K, N, dst, static_cast<cudaStream_t>(stream));
+}
+}  // namespace
+
+int eetq_b200_pack4(const uint8_t* q4_kn, int64_t K, int64_t N, uint8_t* q4_b200, void* stream)
+{
+    return nibble_layout_entry("pack4", NIB_PACK4, q4_kn, K, N, q4_b200, stream);
+}
+int eetq_b200_unpack4(const uint8_t* q4_b200, int64_t K, int64_t N, uint8_t* q4_kn, void* stream)
+{
+    return nibble_layout_entry("unpack4", NIB_UNPACK4, q4_b200, K, N, q4_kn, stream);
+}
+int eetq_b200_from_ref_layout4(const uint8_t* w4_ref, int64_t K, int64_t N, uint8_t* q4_b200, void* stream)
+{
+    return nibble_layout_entry("from_ref_layout4", NIB_FROM_REF4, w4_ref, K, N, q4_b200, stream);
+}
+int eetq_b200_to_ref_layout4(const uint8_t* q4_b200, int64_t K, int64_t N, uint8_t* w4_ref, void* stream)
+{
+    return nibble_layout_entry("to_ref_layout4", NIB_TO_REF4, q4_b200, K, N, w4_ref, stream);
+}
+
+namespace {
+// the tcgen05 scratch comes first (its flag page must stay where the caller zeroed it), the widened weights after it
+size_t w4_tc_scratch_bytes(int64_t M, int64_t N, int64_t K) { return (gemm_tc_workspace_bytes(M, N, K) + 255) & ~size_t(255); }
+}  // namespace
+
+size_t eetq_b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K)
+{
+    if (M <= EETQ_B200_GEMV4_MAX_M || N <= 0 || K <= 0)
+        return 0;
+    return w4_tc_scratch_bytes(M, N, K) + size_t(N) * size_t(K);
+}
+
+int eetq_b200_w4a16_gemm(const void* x, int64_t ldx, const uint8_t* q4_b200, const void* scales, const void* bias, void* y,
+                         int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes,
+                         int flags, void* stream)
+{
+    if (int rc = check_forward_args("w4a16_gemm", x, ldx, q4_b200, scales, y, ldy, M, N, K, dtype))
+        return rc;
+    EB_CHECK_ARG(!(flags & (EETQ_B200_FLAG_FORCE_GEMV | EETQ_B200_FLAG_FORCE_TC)), "w4a16_gemm: FORCE_* flags are not supported");
+    if (M == 0)
+        return EETQ_B200_OK;
+    if (int rc = check_arch())
+        return rc;
+    const bool pdl = (flags & EETQ_B200_FLAG_PDL) != 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (M <= EETQ_B200_GEMV4_MAX_M) {
+        GemvExtras ex;
+        ex.wbits = 4;
+        return launch_gemv(x, ldx, reinterpret_cast<const int8_t*>(q4_b200), scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl, s);
+    }
+    const size_t scratch = w4_tc_scratch_bytes(M, N, K);
+    if (workspace == nullptr || !aligned16(workspace) || workspace_bytes < scratch + size_t(N) * size_t(K)) {
+        set_error("w4a16_gemm: M > %d needs a workspace of %zu bytes (got %zu)", EETQ_B200_GEMV4_MAX_M, scratch + size_t(N) * size_t(K),
+                  workspace_bytes);
+        return EETQ_B200_EWORKSPACE;
+    }
+    int8_t* widened = static_cast<int8_t*>(workspace) + scratch;
+    if (int rc = launch_widen4to8(q4_b200, K, N, widened, s))
+        return rc;
+    return launch_gemm_tc(x, ldx, widened, scales, bias, nullptr, 0, y, ldy, M, N, K, dtype, workspace, scratch, false, nullptr, s);
 }
 
 // Development aid (trace builds only; a no-op otherwise): point the kernels' timeline recorder at a device buffer of

@@ -51,6 +51,11 @@ int launch_quantize(const void* w_kn, int w_dtype, int64_t K, int64_t N, int8_t*
 int launch_transpose_bytes(const int8_t* src, int64_t rows, int64_t cols, int8_t* dst, cudaStream_t stream);
 int launch_from_ref_layout(const uint8_t* w_ref, int64_t K, int64_t N, int8_t* q_b200, cudaStream_t stream);
 int launch_to_ref_layout(const int8_t* q_b200, int64_t K, int64_t N, uint8_t* w_ref, cudaStream_t stream);
+// packed int4 (quantize.cu)
+int launch_quantize4(const void* w_kn, int w_dtype, int64_t K, int64_t N, uint8_t* q4_b200, void* scales, float* s32,
+                     uint8_t* q4_kn, cudaStream_t stream);
+int launch_nibble_layout(int mode, const uint8_t* src, int64_t K, int64_t N, uint8_t* dst, cudaStream_t stream);
+int launch_widen4to8(const uint8_t* q4_b200, int64_t K, int64_t N, int8_t* q_b200, cudaStream_t stream);
 
 enum { GEMV_X_PLAIN = 0, GEMV_X_RMSNORM = 1, GEMV_X_SILU_MUL = 2 };
 enum { GEMV_EPI_PLAIN = 0, GEMV_EPI_SILU_PAIRS = 1 };
@@ -129,6 +134,7 @@ struct GemvExtras {
     // for the kernel after them, which starts its own weight stream sooner (measured +3.3 % decode tokens/s).
     const void* next_w = nullptr;
     int64_t next_n = 0, next_k = 0;
+    int wbits = 8;  // 8: b200 int8 layout; 4: b200 int4 layout (M <= 4)
 };
 int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, void* y, int64_t ldy,
                 int M, int64_t N, int64_t K, int dtype, const GemvExtras& ex, bool pdl, cudaStream_t stream);

@@ -165,7 +165,24 @@ struct XSlice<__half> {
             acc = fhfma(uint16_t(p23 >> 16), uint16_t(h2[2 * q + 1] >> 16), acc);
         }
     }
-    static constexpr float kOffset = 1152.f;  // 1024 (exponent trick) + 128 (storage bias)
+    // int4 (b200 int4 layout): a 32-bit word holds 8 consecutive k; nibble p < 4 is k = 2p, nibble 4 + p is k = 2p + 1, so
+    // (word >> 4p) & 0x000f000f is the adjacent-k pair and OR-ing the exponent pattern gives fp16x2(1024 + u) with u = q + 8:
+    // one shift + one LOP3 per 2 weights, then the same FHFMA pair
+    __device__ __forceinline__ void dot(const uint2& wv, float& acc) const
+    {
+        const uint32_t words[2] = {wv.x, wv.y};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const uint32_t pr = ((words[q] >> (4 * p)) & 0x000f000fu) | 0x64006400u;
+                acc = fhfma(uint16_t(pr & 0xffffu), uint16_t(h2[4 * q + p] & 0xffffu), acc);
+                acc = fhfma(uint16_t(pr >> 16), uint16_t(h2[4 * q + p] >> 16), acc);
+            }
+        }
+    }
+    // 1024 (exponent trick) + storage bias (128 for int8 bytes, 8 for int4 nibbles)
+    static constexpr __host__ __device__ float offset(int wbits) { return wbits == 8 ? 1152.f : 1032.f; }
 };
 
 template <>
@@ -236,7 +253,45 @@ struct XSlice<__nv_bfloat16> {
         }
         acc += a2.x + a2.y;
     }
-    static constexpr float kOffset = 0.f;
+    // int4: nibbles through the same fp32 mantissa trick, (2^23 + u) - (2^23 + 8) = q
+    __device__ __forceinline__ void dot(const uint2& wv, float& acc) const
+    {
+        const uint32_t words[2] = {wv.x, wv.y};
+        float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float2 v;
+                v.x = __uint_as_float(((words[q] >> (4 * p)) & 0xfu) | 0x4B000000u) - 8388616.f;
+                v.y = __uint_as_float(((words[q] >> (4 * p + 16)) & 0xfu) | 0x4B000000u) - 8388616.f;
+                a2  = ffma2(v, f2[4 * q + p], a2);
+            }
+        }
+        acc += a2.x + a2.y;
+    }
+    static constexpr __host__ __device__ float offset(int) { return 0.f; }
+};
+
+// what a thread loads per (row, k-iteration): 16 consecutive k of one output feature
+template <int WB>
+struct WChunk;
+template <>
+struct WChunk<8> {
+    using type = uint4;
+    static __device__ __forceinline__ uint4 load(const uint8_t* p) { return ldg_stream_128(p); }
+    static __device__ __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
+};
+template <>
+struct WChunk<4> {
+    using type = uint2;
+    static __device__ __forceinline__ uint2 load(const uint8_t* p)
+    {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return r;
+    }
+    static __device__ __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
 };
 
 // Sum v[r] over the 32 lanes for all R rows with a transposing butterfly.  On return every lane holds,
@@ -280,6 +335,10 @@ template <>
 struct Log2<8> {
     static constexpr int v = 3;
 };
+template <>
+struct Log2<16> {
+    static constexpr int v = 4;
+};
 
 // dynamic smem: partial[row][m][warp] fp32
 extern __shared__ float gemv_partial[];
@@ -309,11 +368,12 @@ struct GemvFuse {
     int nowait;     // != 0: every input is an LL buffer (data carries its own tag): do not wait for the previous grid to complete
 };
 
-template <typename T, int M, int KITERS, int R, bool XREG>
+template <typename T, int M, int KITERS, int R, bool XREG, int WB>
 __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
     w8a16_gemv_kernel(const T* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ w, const T* __restrict__ scales,
                       const T* __restrict__ bias, T* __restrict__ y, int64_t ldy, int N, int K, const GemvFuse<T> fuse)
 {
+    using WV = typename WChunk<WB>::type;  // 16 k-values of one row: 16 bytes (int8) or 8 bytes (int4)
     __shared__ float red_smem[M][kWarps];
     const int tid     = threadIdx.x;
     const int lane    = tid & 31;
@@ -353,8 +413,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
 
     if constexpr (XREG) {
         // ------------------------------------------------------------------ register-resident activations
-        uint4 wb[2][R][KITERS];
-        auto load_group = [&](uint4 (&buf)[R][KITERS], int g) {
+        WV wb[2][R][KITERS];
+        auto load_group = [&](WV (&buf)[R][KITERS], int g) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int row = row_begin + g * R + r;
@@ -362,9 +422,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
                 for (int i = 0; i < KITERS; ++i) {
                     const int c = tid + i * kThreads;
                     if (row < row_end && c < nchunks)
-                        buf[r][i] = ldg_stream_128(w + int64_t(row) * K + int64_t(c) * 16);
+                        buf[r][i] = WChunk<WB>::load(w + ((int64_t(row) * K + int64_t(c) * 16) * WB >> 3));
                     else
-                        buf[r][i] = make_uint4(0u, 0u, 0u, 0u);
+                        buf[r][i] = WChunk<WB>::zero();
                 }
             }
         };
@@ -483,11 +543,11 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
 #pragma unroll
             for (int i = 0; i < KITERS; ++i)
                 so += xs[m][i].sum;
-            xoff[m] = -XSlice<T>::kOffset * so;
+            xoff[m] = -XSlice<T>::offset(WB) * so;
         }
 
         trace_ev(TRACE_GEMV, 3);
-        auto compute_group = [&](uint4 (&buf)[R][KITERS], int g) {
+        auto compute_group = [&](WV (&buf)[R][KITERS], int g) {
             float acc[M][R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -529,18 +589,18 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
                 const int c = tid + i * kThreads;
                 if (c >= nchunks)
                     break;
-                uint4 buf[R];
+                WV buf[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int row = row_begin + g * R + r;
-                    buf[r]        = (row < row_end) ? ldg_stream_128(w + int64_t(row) * K + int64_t(c) * 16)
-                                                    : make_uint4(0u, 0u, 0u, 0u);
+                    buf[r]        = (row < row_end) ? WChunk<WB>::load(w + ((int64_t(row) * K + int64_t(c) * 16) * WB >> 3))
+                                                    : WChunk<WB>::zero();
                 }
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
                     XSlice<T> xv;
                     xv.load(x + int64_t(m) * ldx + int64_t(c) * 16);
-                    const float off = -XSlice<T>::kOffset * xv.sum;
+                    const float off = -XSlice<T>::offset(WB) * xv.sum;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         float a = off;
@@ -656,7 +716,7 @@ int gemv_grid(int sm_count, int ctas_per_sm, int N, int align)
     return grid;
 }
 
-template <typename T, int M, int KITERS, int R, bool XREG>
+template <typename T, int M, int KITERS, int R, bool XREG, int WB>
 int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N,
                    int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
@@ -684,7 +744,7 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
     cfg.numAttrs                                       = pdl ? 1 : 0;
 
     const cudaError_t e =
-        cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG>, x, ldx, w, scales, bias, y, ldy, N, K, fuse);
+        cudaLaunchKernelEx(&cfg, w8a16_gemv_kernel<T, M, KITERS, R, XREG, WB>, x, ldx, w, scales, bias, y, ldy, N, K, fuse);
     count_launch();
     if (e != cudaSuccess) {
         set_error("gemv launch failed: %s", cudaGetErrorString(e));
@@ -693,7 +753,7 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
     return EETQ_B200_OK;
 }
 
-template <typename T, int M>
+template <typename T, int M, int WB>
 int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N, int K,
                const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
@@ -701,11 +761,13 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     const int kiters  = (nchunks + kThreads - 1) / kThreads;
     // register-resident activations while the slice stays small (fp16: 8 regs, bf16: 16 regs per 16 values)
     constexpr int kMaxXregIters = (DTypeOf<T>::value == EETQ_B200_F16) ? 8 / M : 4 / M;
+    // int4 rows are half as long: twice the rows per group keep the same number of bytes in flight per thread
+    constexpr int kRMul = (WB == 4) ? 2 : 1;
 #define EB_GEMV_CASE(KI, RS, RB)                                                                                        \
     if (kiters == KI) {                                                                                                 \
         if constexpr (KI <= kMaxXregIters)                                                                             \
-            return launch_variant<T, M, KI, (M <= 2 ? RS : RB), true>(x, ldx, w, scales, bias, y, ldy, N, K, fuse,     \
-                                                                      pdl, stream);                                     \
+            return launch_variant<T, M, KI, kRMul * (M <= 2 ? RS : RB), true, WB>(x, ldx, w, scales, bias, y, ldy, N, K,   \
+                                                                                  fuse, pdl, stream);                   \
     }
     EB_GEMV_CASE(1, 8, 4)
     EB_GEMV_CASE(2, 4, 2)
@@ -718,24 +780,31 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
         return EETQ_B200_EINVAL;
     }
     constexpr int R = (M <= 2) ? 8 : 4;
-    return launch_variant<T, M, 1, R, false>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+    return launch_variant<T, M, 1, R, false, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
 }
 
-template <typename T>
+template <typename T, int WB>
 int dispatch_m(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
                int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
     switch (M) {
-        case 1: return dispatch_k<T, 1>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 2: return dispatch_k<T, 2>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 3: return dispatch_k<T, 3>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 4: return dispatch_k<T, 4>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 5: return dispatch_k<T, 5>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 6: return dispatch_k<T, 6>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 7: return dispatch_k<T, 7>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 8: return dispatch_k<T, 8>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        default: set_error("gemv: M=%d out of range [1,%d]", M, EETQ_B200_GEMV_MAX_M); return EETQ_B200_EINVAL;
+        case 1: return dispatch_k<T, 1, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 2: return dispatch_k<T, 2, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 3: return dispatch_k<T, 3, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 4: return dispatch_k<T, 4, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        default: break;
     }
+    if constexpr (WB == 8) {
+        switch (M) {
+            case 5: return dispatch_k<T, 5, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 6: return dispatch_k<T, 6, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 7: return dispatch_k<T, 7, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 8: return dispatch_k<T, 8, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            default: break;
+        }
+    }
+    set_error("gemv: M=%d out of range [1,%d]", M, WB == 8 ? EETQ_B200_GEMV_MAX_M : EETQ_B200_GEMV4_MAX_M);
+    return EETQ_B200_EINVAL;
 }
 
 template <typename T>
@@ -800,15 +869,25 @@ int launch_gemv(const void* x, int64_t ldx, const int8_t* w, const void* scales,
         set_error("gemv: the SiLU*up pair epilogue takes no bias and needs N %% 4 == 0");
         return EETQ_B200_EINVAL;
     }
+    if (ex.wbits != 8 && ex.wbits != 4) {
+        set_error("gemv: weights must be 8 or 4 bits wide (got %d)", ex.wbits);
+        return EETQ_B200_EINVAL;
+    }
     if (dtype == EETQ_B200_F16) {
         using T = __half;
-        return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
-                             static_cast<T*>(y), ldy, M, int(N), int(K), make_fuse<T>(ex), pdl, stream);
+        if (ex.wbits == 4)
+            return dispatch_m<T, 4>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
+                                    static_cast<T*>(y), ldy, M, int(N), int(K), make_fuse<T>(ex), pdl, stream);
+        return dispatch_m<T, 8>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
+                                static_cast<T*>(y), ldy, M, int(N), int(K), make_fuse<T>(ex), pdl, stream);
     }
     if (dtype == EETQ_B200_BF16) {
         using T = __nv_bfloat16;
-        return dispatch_m<T>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
-                             static_cast<T*>(y), ldy, M, int(N), int(K), make_fuse<T>(ex), pdl, stream);
+        if (ex.wbits == 4)
+            return dispatch_m<T, 4>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
+                                    static_cast<T*>(y), ldy, M, int(N), int(K), make_fuse<T>(ex), pdl, stream);
+        return dispatch_m<T, 8>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
+                                static_cast<T*>(y), ldy, M, int(N), int(K), make_fuse<T>(ex), pdl, stream);
     }
     set_error("gemv: unsupported activation dtype %d", dtype);
     return EETQ_B200_EINVAL;

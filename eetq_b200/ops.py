@@ -14,8 +14,9 @@ Same names, arity, argument meaning and return order as the reference (fpA_intB_
   reference requires (results come back on the CPU), CUDA inputs are an extension (results stay on the device);
 * ``w8_a16_gemm`` validates dtype / device / contiguity / shape agreement (the reference validates nothing) and
   accepts bf16 as well as fp16;
-* int4 (``torch.quint4x2`` / ``is_int4=True``) raises NotImplementedError -- unreachable from the reference's own
-  Python (fpA_intB_gemm_wrapper.cu:154-159 hard-codes Int8b).
+* packed int4 (``quant_weights(w, torch.quint4x2)`` / ``preprocess_weights(w, is_int4=True)``) is supported with the reference's
+  shapes (``[K, N/2]`` int8, two values per byte) and bit-exact values; the reference has no Python-visible int4 GEMM
+  (fpA_intB_gemm_wrapper.cu:154-159 hard-codes Int8b), ``w4_a16_gemm`` is this repository's addition.
 """
 from __future__ import annotations
 
@@ -27,7 +28,8 @@ import torch
 from . import _cabi
 
 __all__ = ["quant_weights", "preprocess_weights", "w8_a16_gemm", "w8_a16_gemm_", "w8_a16_gemm_bias", "w8_a16_gemm_residual",
-           "convert_ref_checkpoint_weight", "to_ref_checkpoint_weight", "unpack_weights", "rotary_embedding_neox", "layernorm_forward"]
+           "convert_ref_checkpoint_weight", "to_ref_checkpoint_weight", "unpack_weights", "rotary_embedding_neox", "layernorm_forward",
+           "w4_a16_gemm", "unpack_weights4", "convert_ref_checkpoint_weight4", "to_ref_checkpoint_weight4"]
 
 _DTYPE_CODE = {torch.float16: _cabi.F16, torch.bfloat16: _cabi.BF16, torch.float32: _cabi.F32}
 
@@ -75,9 +77,8 @@ def _workspace(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
 # ---------------------------------------------------------------------------------------------------------------
 def quant_weights(origin_weight: torch.Tensor, quant_type, return_unprocessed_quantized_tensor: bool = False) -> List[torch.Tensor]:
     w = origin_weight
-    if quant_type in (getattr(torch, "quint4x2", None),):
-        raise NotImplementedError("int4 weight-only quantisation is not implemented in eetq_b200")
-    if quant_type != torch.int8:
+    int4 = quant_type == getattr(torch, "quint4x2", None)
+    if quant_type != torch.int8 and not int4:
         raise RuntimeError("Must be int4 or int8 quantization")  # same message as the reference (wrapper.cu:41)
     if w.numel() == 0:
         raise RuntimeError("weight should not be empty tensor")
@@ -95,8 +96,10 @@ def quant_weights(origin_weight: torch.Tensor, quant_type, return_unprocessed_qu
     experts = 1 if w.dim() == 2 else w.shape[0]
     with torch.cuda.device(dev):
         wd = w.to(dev, non_blocking=False)
-        processed = torch.empty(w.shape, dtype=torch.int8, device=dev)
-        unprocessed = torch.empty(w.shape, dtype=torch.int8, device=dev) if return_unprocessed_quantized_tensor else None
+        # int4: two values per byte along the last axis, like the reference's [.., K, N/2] tensors (wrapper.cu:48-63)
+        qshape = w.shape[:-1] + (N // 2,) if int4 else w.shape
+        processed = torch.empty(qshape, dtype=torch.int8, device=dev)
+        unprocessed = torch.empty(qshape, dtype=torch.int8, device=dev) if return_unprocessed_quantized_tensor else None
         scales = torch.empty(w.shape[:-2] + (N,), dtype=w.dtype, device=dev)
         s32 = torch.empty(experts, N, dtype=torch.float32, device=dev)
         L = _cabi.lib()
@@ -105,8 +108,9 @@ def quant_weights(origin_weight: torch.Tensor, quant_type, return_unprocessed_qu
             pe = processed if w.dim() == 2 else processed[e]
             ue = None if unprocessed is None else (unprocessed if w.dim() == 2 else unprocessed[e])
             se = scales if w.dim() == 2 else scales[e]
-            rc = L.eetq_b200_quantize(_vp(we), _DTYPE_CODE[w.dtype], K, N, _vp(pe), _vp(se), _vp(s32[e]), _vp(ue), _stream())
-            _cabi.check(rc, "eetq_b200_quantize")
+            fn = L.eetq_b200_quantize4 if int4 else L.eetq_b200_quantize
+            rc = fn(_vp(we), _DTYPE_CODE[w.dtype], K, N, _vp(pe), _vp(se), _vp(s32[e]), _vp(ue), _stream())
+            _cabi.check(rc, "eetq_b200_quantize4" if int4 else "eetq_b200_quantize")
     if on_cpu:
         processed, scales = processed.cpu(), scales.cpu()
         unprocessed = None if unprocessed is None else unprocessed.cpu()
@@ -118,12 +122,14 @@ def quant_weights(origin_weight: torch.Tensor, quant_type, return_unprocessed_qu
 # ---------------------------------------------------------------------------------------------------------------
 # preprocess_weights  (preprocess_weights_cuda, fpA_intB_gemm_wrapper.cu:109-128)
 # ---------------------------------------------------------------------------------------------------------------
-def _layout_call(fn_name: str, t: torch.Tensor) -> torch.Tensor:
+def _layout_call(fn_name: str, t: torch.Tensor, int4: bool = False) -> torch.Tensor:
     if t.dtype not in (torch.int8, torch.uint8) or t.dim() != 2:
         raise RuntimeError(f"{fn_name}: expected a 2-D int8 tensor")
     on_cpu = not t.is_cuda
     dev = _default_device() if on_cpu else t.device
     K, N = t.shape
+    if int4:
+        N *= 2  # [K, N/2] bytes hold K x N values
     with torch.cuda.device(dev):
         src = t.contiguous().to(dev)
         dst = torch.empty_like(src)
@@ -135,13 +141,31 @@ def _layout_call(fn_name: str, t: torch.Tensor) -> torch.Tensor:
 def preprocess_weights(origin_weight: torch.Tensor, is_int4: bool = False) -> torch.Tensor:
     """Row-major int8 ``[K, N]`` -> kernel layout (b200), returned with the same nominal shape like the reference."""
     if is_int4:
-        raise NotImplementedError("int4 weights are not implemented in eetq_b200")
+        # packed row-major [K, N/2] (low nibble = even column) -> b200 int4 layout.  The reference passes the BYTE column count
+        # as the element count here (fpA_intB_gemm_wrapper.cu:121-126) and so rearranges only the first half of the buffer;
+        # this converts the whole matrix
+        return _layout_call("eetq_b200_pack4", origin_weight, int4=True)
     return _layout_call("eetq_b200_pack", origin_weight)
 
 
 def unpack_weights(weight: torch.Tensor) -> torch.Tensor:
     """Inverse of :func:`preprocess_weights` (b200 layout -> row-major int8 ``[K, N]``)."""
     return _layout_call("eetq_b200_unpack", weight)
+
+
+def unpack_weights4(weight: torch.Tensor) -> torch.Tensor:
+    """b200 int4 layout ``[K, N/2]`` -> packed row-major ``[K, N/2]`` (two's-complement nibbles, low nibble = even column)."""
+    return _layout_call("eetq_b200_unpack4", weight, int4=True)
+
+
+def convert_ref_checkpoint_weight4(weight_ref: torch.Tensor) -> torch.Tensor:
+    """The reference's processed int4 bytes (``quant_weights(w, torch.quint4x2)[0]`` of an EETQ build, sm80 layout,
+    cutlass_preprocessors.cc:497-534) -> b200 int4 layout."""
+    return _layout_call("eetq_b200_from_ref_layout4", weight_ref.view(torch.int8), int4=True)
+
+
+def to_ref_checkpoint_weight4(weight: torch.Tensor) -> torch.Tensor:
+    return _layout_call("eetq_b200_to_ref_layout4", weight, int4=True)
 
 
 def convert_ref_checkpoint_weight(weight_ref: torch.Tensor) -> torch.Tensor:
@@ -235,6 +259,38 @@ def w8_a16_gemm_residual(input: torch.Tensor, weight: torch.Tensor, scale: torch
     if M > 0:
         with torch.cuda.device(input.device):
             _gemm_into(x2, weight, scale, bias, out.view(-1, N), M, N, K, residual=r2)
+    return out
+
+
+def w4_a16_gemm(input: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``y = input @ dequant(weight)`` for packed-int4 weights in the b200 int4 layout (``[K, N/2]`` int8 from
+    ``quant_weights(w, torch.quint4x2)`` / ``preprocess_weights(w, is_int4=True)``).  Same arithmetic as ``w8_a16_gemm`` with q in
+    [-8, 7]; what the reference's compiled-but-unselectable Int4b kernels compute (weightOnlyBatchedGemv/kernel.h:68-116)."""
+    if weight.dtype != torch.int8 or weight.dim() != 2:
+        raise RuntimeError("w4_a16_gemm: weight must be a 2-D int8 tensor [K, N/2]")
+    K, N = weight.shape[0], weight.shape[1] * 2
+    if not input.is_cuda:
+        raise RuntimeError("w4_a16_gemm: input must be a CUDA tensor (eetq_b200 has no CPU path)")
+    if input.dtype not in (torch.float16, torch.bfloat16) or scale.dtype != input.dtype or (bias is not None and bias.dtype != input.dtype):
+        raise RuntimeError("w4_a16_gemm: input, scale (and bias) must share dtype float16 or bfloat16")
+    if input.shape[-1] != K or scale.numel() != N or (bias is not None and bias.numel() != N):
+        raise RuntimeError(f"w4_a16_gemm: shapes do not match K={K}, N={N}")
+    if any(t.device != input.device for t in (weight, scale) + (() if bias is None else (bias,))):
+        raise RuntimeError("w4_a16_gemm: all tensors must be on the same device")
+    if not weight.is_contiguous() or not scale.is_contiguous() or (bias is not None and not bias.is_contiguous()):
+        raise RuntimeError("w4_a16_gemm: weight, scale and bias must be contiguous")
+    x2 = input.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0) or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    out = torch.empty(input.shape[:-1] + (N,), dtype=input.dtype, device=input.device)
+    if M > 0:
+        with torch.cuda.device(input.device):
+            L = _cabi.lib()
+            ws = _workspace(input.device, int(L.eetq_b200_w4a16_workspace_bytes(M, N, K)))
+            rc = L.eetq_b200_w4a16_gemm(_vp(x2), x2.stride(0) if M > 1 else K, _vp(weight), _vp(scale), _vp(bias), _vp(out), N, M, N, K,
+                                        _DTYPE_CODE[input.dtype], _vp(ws), 0 if ws is None else ws.numel(), _cabi.FLAG_DEFAULT, _stream())
+            _cabi.check(rc, "eetq_b200_w4a16_gemm")
     return out
 
 

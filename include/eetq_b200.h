@@ -252,6 +252,42 @@ int eetq_b200_lm_head_argmax(const void* x, const eetq_b200_ll* x_ll, const void
                              int64_t H, int64_t v_begin, void* logits, void* scratch, void* token_i64, void* pos_i32, void* step_i32,
                              const eetq_b200_ll_push* cand, int rank, int pdl, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Packed int4 weights (QuantType::PACKED_INT4_WEIGHT_ONLY).  In the reference int4 is reachable from Python only as
+ * quant_weights(w, torch.quint4x2, ..) and preprocess_weights(w, is_int4=True) (csrc/eetpy.cpp:11-17): its w8_a16_gemm
+ * hard-codes Int8b (fpA_intB_gemm_wrapper.cu:154-159) although the int4 kernels are compiled into the extension
+ * (weightOnlyBatchedGemv/kernel.h:68-116, ...Bs{1..4}Int4b.cu).  Here both halves exist.
+ *
+ * "b200 int4 layout": K*N/2 bytes, output-feature-major rows of K/2 bytes; in every 32-bit word (8 consecutive k of
+ * one output feature) nibble p < 4 holds q[8j + 2p] + 8 and nibble 4 + p holds q[8j + 2p + 1] + 8, so that
+ * (word >> 4p) & 0x000f000f is the adjacent-k pair (the reference interleaves nibbles the same way for the same reason,
+ * cutlass_preprocessors.cc:389-417).  Packed row-major ("unprocessed") tensors are [K, N/2] bytes, low nibble = even
+ * column (cutlass_preprocessors.cc:651-669).
+ * ------------------------------------------------------------------------------------------- */
+#define EETQ_B200_GEMV4_MAX_M 4
+
+/* quant_weights(w, quint4x2): s32[n] = amax[n] * (1/8); q = clamp(int(round_half_away(w / s32[n])), -8, 7), NaN -> -8
+ * (bit-exact with ft::symmetric_quantize, cutlass_preprocessors.cc:608-669).  q4_b200: K*N/2 bytes out;
+ * q4_kn: packed row-major [K, N/2] out or NULL; scales / s32 as in eetq_b200_quantize. */
+int eetq_b200_quantize4(const void* w_kn, int w_dtype, int64_t K, int64_t N, uint8_t* q4_b200, void* scales, float* s32,
+                        uint8_t* q4_kn, void* stream);
+/* preprocess_weights(w, is_int4=True): packed row-major [K, N/2] -> b200 int4 layout, and its inverse */
+int eetq_b200_pack4(const uint8_t* q4_kn, int64_t K, int64_t N, uint8_t* q4_b200, void* stream);
+int eetq_b200_unpack4(const uint8_t* q4_b200, int64_t K, int64_t N, uint8_t* q4_kn, void* stream);
+/* checkpoint compatibility: the reference's sm75..sm89 int4 bytes (preprocess_weights_for_mixed_gemm with
+ * PACKED_INT4_WEIGHT_ONLY, cutlass_preprocessors.cc:497-534) <-> b200 int4 layout */
+int eetq_b200_from_ref_layout4(const uint8_t* w4_ref, int64_t K, int64_t N, uint8_t* q4_b200, void* stream);
+int eetq_b200_to_ref_layout4(const uint8_t* q4_b200, int64_t K, int64_t N, uint8_t* w4_ref, void* stream);
+/* y = dtype( sum_k x[m,k] * q[k,n] * s[n] ) (+ bias) with int4 weights.  M <= EETQ_B200_GEMV4_MAX_M streams the nibbles
+ * straight through the decode kernel (half the HBM bytes of w8a16).  Larger M first widens the weights to the b200 int8
+ * layout in `workspace` (one extra HBM pass of 1.5 * K*N/1 bytes, negligible next to the tensor-core GEMM it feeds), then
+ * runs the tcgen05 kernel: workspace must hold eetq_b200_w4a16_workspace_bytes(M,N,K) bytes (zero-initialised once), else
+ * EETQ_B200_EWORKSPACE. */
+size_t eetq_b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int eetq_b200_w4a16_gemm(const void* x, int64_t ldx, const uint8_t* q4_b200, const void* scales, const void* bias, void* y,
+                         int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes,
+                         int flags, void* stream);
+
 /* number of kernels this library has launched on this process so far (bench.py's gpu_launches) */
 uint64_t eetq_b200_launch_count(void);
 

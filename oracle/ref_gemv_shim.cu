@@ -12,8 +12,8 @@
 
 #include "weightOnlyBatchedGemv/kernelLauncher.h"
 
-extern "C" int ref_w8a16_gemv(const void* x, const void* w_ref_layout, const void* scales, void* y, int m, int n, int k,
-                              void* stream)
+static int ref_gemv_any(const void* x, const void* w_ref_layout, const void* scales, void* y, int m, int n, int k,
+                        tensorrt_llm::kernels::WeightOnlyQuantType qtype, void* stream)
 {
     namespace trt = tensorrt_llm::kernels;
     if (m < 1 || m > 4)
@@ -29,10 +29,24 @@ extern "C" int ref_w8a16_gemv(const void* x, const void* w_ref_layout, const voi
                                  n,
                                  k,
                                  0,
-                                 trt::WeightOnlyQuantType::Int8b,
+                                 qtype,
                                  trt::WeightOnlyType::PerChannel,
                                  trt::WeightOnlyActivationFunctionType::Identity,
                                  trt::WeightOnlyActivationType::FP16};
     trt::weight_only_batched_gemv_launcher(params, static_cast<cudaStream_t>(stream));
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+extern "C" int ref_w8a16_gemv(const void* x, const void* w_ref_layout, const void* scales, void* y, int m, int n, int k,
+                              void* stream)
+{
+    return ref_gemv_any(x, w_ref_layout, scales, y, m, n, k, tensorrt_llm::kernels::WeightOnlyQuantType::Int8b, stream);
+}
+
+// same kernel template, Int4b weights in the reference's int4 layout (kernel.h:68-116); not selectable from the reference's
+// Python (fpA_intB_gemm_wrapper.cu:154-159 hard-codes Int8b) but compiled into its extension
+extern "C" int ref_w4a16_gemv(const void* x, const void* w_ref_layout, const void* scales, void* y, int m, int n, int k,
+                              void* stream)
+{
+    return ref_gemv_any(x, w_ref_layout, scales, y, m, n, k, tensorrt_llm::kernels::WeightOnlyQuantType::Int4b, stream);
 }

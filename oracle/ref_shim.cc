@@ -73,3 +73,45 @@ extern "C" int ref_preprocess(int8_t* out, const int8_t* in, size_t K, size_t N)
         return 1;
     }
 }
+
+// ---- packed int4 (QuantType::PACKED_INT4_WEIGHT_ONLY): reachable from the reference's Python as
+// quant_weights(w, torch.quint4x2, ...) and preprocess_weights(w, is_int4=True)  (csrc/eetpy.cpp:11-17) ----
+// quant_weights(w[K,N] fp16, quint4x2) -> processed / unprocessed packed [K, N/2] (two int4 per byte), scales fp16[N]
+extern "C" int ref_quant4_fp16(int8_t* processed, int8_t* unprocessed, void* scales, const void* w, size_t K, size_t N)
+{
+    try {
+        ft::symmetric_quantize<half, half>(processed, unprocessed, static_cast<half*>(scales),
+                                           static_cast<const half*>(w), {K, N}, ft::QuantType::PACKED_INT4_WEIGHT_ONLY);
+        return 0;
+    }
+    catch (std::exception& e) {
+        fprintf(stderr, "ref_quant4_fp16: %s\n", e.what());
+        return 1;
+    }
+}
+
+extern "C" int ref_quant4_fp32(int8_t* processed, int8_t* unprocessed, float* scales, const float* w, size_t K, size_t N)
+{
+    try {
+        ft::symmetric_quantize<float, float>(processed, unprocessed, scales, w, {K, N},
+                                             ft::QuantType::PACKED_INT4_WEIGHT_ONLY);
+        return 0;
+    }
+    catch (std::exception& e) {
+        fprintf(stderr, "ref_quant4_fp32: %s\n", e.what());
+        return 1;
+    }
+}
+
+// preprocess_weights(packed int4 row-major, K x N ELEMENTS = K*N/2 bytes, is_int4=true) -> reference sm80 int4 layout
+extern "C" int ref_preprocess4(int8_t* out, const int8_t* in, size_t K, size_t N)
+{
+    try {
+        ft::preprocess_weights(out, in, K, N, /*is_int4=*/true, /*arch=*/80);
+        return 0;
+    }
+    catch (std::exception& e) {
+        fprintf(stderr, "ref_preprocess4: %s\n", e.what());
+        return 1;
+    }
+}

@@ -165,3 +165,125 @@ void oracle_gemm_f64(const f16* x, const int8_t* q_kn, const f16* s, double* y, 
         }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Packed int4 (QuantType::PACKED_INT4_WEIGHT_ONLY) -- reachable from the reference's Python as
+ * quant_weights(w, torch.quint4x2, ..) and preprocess_weights(w, is_int4=True) (csrc/eetpy.cpp:11-17).
+ * Quantiser: cutlass_preprocessors.cc:608-669
+ *   s32[n] = amax[n] * (1/8);  v = (int)round(float(w)/s32[n]);  q = max(-8, min(7, v));
+ *   two values per byte: low nibble = even column, high nibble = odd column.
+ *   The float->int conversion happens BEFORE the clamp; for NaN (0/0 in an all-zero column, or a NaN weight)
+ *   x86-64's cvttss2si returns INT_MIN, which clamps to -8.  Written out explicitly here so the restatement
+ *   does not depend on the host's conversion behaviour.
+ * ------------------------------------------------------------------------------------------- */
+static inline int quant_one4(float w, float s32)
+{
+    float r = roundf(w / s32);
+    if (r != r) return -8; /* NaN -> INT_MIN -> -8 */
+    int v = (r > 100.f) ? 100 : (r < -100.f) ? -100 : (int)r;
+    return v < -8 ? -8 : (v > 7 ? 7 : v);
+}
+
+void oracle_quantize4_f32(const float* w, size_t K, size_t N, uint8_t* packed_kn2, float* scales_f32)
+{
+    for (size_t n = 0; n < N; ++n) {
+        float amax = 0.f;
+        for (size_t k = 0; k < K; ++k) {
+            float a = fabsf(w[k * N + n]);
+            if (amax < a) amax = a;
+        }
+        scales_f32[n] = amax * (1.f / 8.f);
+    }
+    for (size_t k = 0; k < K; ++k)
+        for (size_t j = 0; j < N / 2; ++j) {
+            int a = quant_one4(w[k * N + 2 * j], scales_f32[2 * j]);
+            int b = quant_one4(w[k * N + 2 * j + 1], scales_f32[2 * j + 1]);
+            packed_kn2[k * (N / 2) + j] = (uint8_t)((a & 15) | ((b & 15) << 4));
+        }
+}
+
+void oracle_quantize4_f16(const f16* w, size_t K, size_t N, uint8_t* packed_kn2, f16* scales_f16, float* scales_f32)
+{
+    for (size_t n = 0; n < N; ++n) {
+        float amax = 0.f;
+        for (size_t k = 0; k < K; ++k) {
+            float a = fabsf((float)w[k * N + n]);
+            if (amax < a) amax = a;
+        }
+        scales_f32[n] = amax * (1.f / 8.f);
+        scales_f16[n] = (f16)scales_f32[n];
+    }
+    for (size_t k = 0; k < K; ++k)
+        for (size_t j = 0; j < N / 2; ++j) {
+            int a = quant_one4((float)w[k * N + 2 * j], scales_f32[2 * j]);
+            int b = quant_one4((float)w[k * N + 2 * j + 1], scales_f32[2 * j + 1]);
+            packed_kn2[k * (N / 2) + j] = (uint8_t)((a & 15) | ((b & 15) << 4));
+        }
+}
+
+static inline int get_nib(const uint8_t* p, size_t i) { return (p[i >> 1] >> (4 * (i & 1))) & 15; }
+static inline void put_nib(uint8_t* p, size_t i, int v)
+{
+    p[i >> 1] = (uint8_t)((p[i >> 1] & (0xF0 >> (4 * (i & 1)))) | ((v & 15) << (4 * (i & 1))));
+}
+
+/* Reference int4 layout for sm75..sm89 (preprocess_weights_for_mixed_gemm, cutlass_preprocessors.cc:497-534, int4 case):
+ *   row permutation in groups of 32 k (:137-195), element transpose (:201-320), ColumnMajorTileInterleave<64,4> (:432-495),
+ *   +8 bias and nibble interleave inside each 32-bit word (:360-418).
+ * Written per OUTPUT nibble: nibble index o = (((n4*(K/64) + kt)*4 + c)*8 + v)*8 + d holds
+ *   (q[perm(64*kt + 8*v + e), 4*n4 + c] + 8) & 15,  e = d<4 ? 2d : 2(d-4)+1,
+ *   perm(k') = 32*(k'/32) + 8*((t%8)/2) + t%2 + 2*(t/8),  t = k' % 32.
+ * Input: packed row-major [K][N/2]; output K*N/2 bytes. */
+int oracle_ref_layout4(const uint8_t* packed_kn2, size_t K, size_t N, uint8_t* out)
+{
+    if (K % 64 || N % 64) return -1;
+    memset(out, 0, K * N / 2);
+    size_t o = 0;
+    for (size_t n4 = 0; n4 < N / 4; ++n4)
+        for (size_t kt = 0; kt < K / 64; ++kt)
+            for (size_t c = 0; c < 4; ++c)
+                for (size_t v = 0; v < 8; ++v)
+                    for (size_t d = 0; d < 8; ++d, ++o) {
+                        size_t e  = d < 4 ? 2 * d : 2 * (d - 4) + 1;
+                        size_t kp = 64 * kt + 8 * v + e;
+                        size_t t  = kp % 32;
+                        size_t k  = 32 * (kp / 32) + 8 * ((t % 8) / 2) + t % 2 + 2 * (t / 8);
+                        size_t n  = 4 * n4 + c;
+                        int q     = get_nib(packed_kn2, k * N + n); /* two's-complement nibble */
+                        put_nib(out, o, (q + 8) & 15);
+                    }
+    return 0;
+}
+
+/* The int4 layout THIS repository's kernels consume: output-feature-major rows of K/2 bytes; in each
+ * 32-bit word (8 consecutive k) nibble p < 4 holds q[8j+2p]+8 and nibble 4+p holds q[8j+2p+1]+8. */
+void oracle_b200_layout4(const uint8_t* packed_kn2, size_t K, size_t N, uint8_t* out)
+{
+    memset(out, 0, K * N / 2);
+    for (size_t n = 0; n < N; ++n)
+        for (size_t k = 0; k < K; ++k) {
+            size_t j = k / 8, r = k % 8;
+            size_t nib = (r & 1) ? 4 + r / 2 : r / 2;
+            int q = get_nib(packed_kn2, k * N + n);
+            put_nib(out, (n * (K / 8) + j) * 8 + nib, (q + 8) & 15);
+        }
+}
+
+/* w4a16 GEMM arithmetic: identical to oracle_gemm_f16 with q in [-8, 7] read from the packed row-major form
+ * (the reference's Int4b decode kernel dequantises the same way: fp16(q) * s, kernel.h:68-116, :355-377). */
+void oracle_gemm4_f16(const f16* x, const uint8_t* packed_kn2, const f16* s, f16* y, size_t M, size_t N, size_t K)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t n = 0; n < N; ++n) {
+        for (size_t m = 0; m < M; ++m) {
+            float acc = 0.f;
+            for (size_t k = 0; k < K; ++k) {
+                int q  = get_nib(packed_kn2, k * N + n);
+                q      = q >= 8 ? q - 16 : q;
+                f16 wd = (f16)((f16)q * s[n]);
+                acc += (float)x[m * K + k] * (float)wd;
+            }
+            y[m * N + n] = (f16)acc;
+        }
+    }
+}

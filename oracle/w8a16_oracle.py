@@ -106,6 +106,102 @@ def b200_layout_inv(w_b200: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# packed int4 (QuantType::PACKED_INT4_WEIGHT_ONLY) -- quant_weights(w, torch.quint4x2) / preprocess_weights(w, is_int4=True)
+# ------------------------------------------------------------------------------------------------
+def pack_int4(q_kn: torch.Tensor) -> torch.Tensor:
+    """int8 values in [-8, 7], ``[.., K, N]`` -> the reference's packed form ``[.., K, N/2]`` int8: low nibble = even column,
+    high nibble = odd column (cutlass_preprocessors.cc:651-669)."""
+    u = (q_kn.to(torch.int16) & 0xF).to(torch.uint8)
+    return (u[..., 0::2] | (u[..., 1::2] << 4)).view(torch.int8).contiguous()
+
+
+def unpack_int4(p_kn2: torch.Tensor) -> torch.Tensor:
+    """Inverse of :func:`pack_int4`: ``[.., K, N/2]`` packed -> sign-extended int8 ``[.., K, N]``."""
+    u = p_kn2.contiguous().view(torch.uint8)
+    lo = (u & 0xF).to(torch.int16)
+    hi = (u >> 4).to(torch.int16)
+    q = torch.stack([lo, hi], dim=-1).reshape(*u.shape[:-1], u.shape[-1] * 2)
+    return (((q + 8) & 0xF) - 8).to(torch.int8)
+
+
+def quantize4(w_kn: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``quant_weights(w, torch.quint4x2)`` arithmetic (cutlass_preprocessors.cc:608-669).
+
+    Returns ``(packed int8 [..,K,N/2], scales (dtype of w) [..,N], s32 fp32 [..,N], q int8 [..,K,N] in [-8,7])``.
+    ``s32 = amax * (1/8)``; ``q = clamp(int(round_half_away(w / s32)), -8, 7)``.  The reference converts the rounded float to
+    ``int`` BEFORE clamping (:658-659); for NaN (an all-zero column: 0/0, or a NaN weight) that conversion yields INT_MIN on
+    x86-64 (cvttss2si's "integer indefinite"), which clamps to -8 -- pinned against the compiled reference in tests/test_oracle.py."""
+    assert w_kn.dtype in (torch.float16, torch.float32) and w_kn.dim() in (2, 3)
+    wf = w_kn.float()
+    s32 = torch.nan_to_num(wf.abs(), nan=0.0, posinf=float("inf")).amax(dim=-2) * np.float32(1.0 / 8.0)
+    r = wf / s32.unsqueeze(-2)
+    r = torch.where(r >= 0, torch.floor(r + 0.5), torch.ceil(r - 0.5))
+    r = torch.where(torch.isnan(r), torch.full_like(r, -8.0), r)
+    q = torch.clamp(r, -8, 7).to(torch.int8)
+    return pack_int4(q), s32.to(w_kn.dtype), s32, q
+
+
+# rows of each group of 32 are read in this order by permute_B_rows_for_mixed_gemm (cutlass_preprocessors.cc:137-195, int4 case)
+_REF_ROW_PERM4 = torch.tensor([8 * ((t % 8) // 2) + t % 2 + 2 * (t // 8) for t in range(32)])
+# destination nibble d of every 32-bit word takes source nibble _REF_NIB4[d] (add_bias_and_interleave_int4s_inplace, :360-418)
+_REF_NIB4 = torch.tensor([0, 2, 4, 6, 1, 3, 5, 7])
+
+
+def ref_layout4(q_kn: torch.Tensor) -> torch.Tensor:
+    """int4 values ``[K, N]`` (int8 in [-8, 7]) -> the reference's sm80 int4 bytes, shaped ``[K, N/2]`` int8.
+
+    Closed form of preprocess_weights_for_mixed_gemm for PACKED_INT4_WEIGHT_ONLY (cutlass_preprocessors.cc:497-534): row
+    permutation inside groups of 32 k, element transpose, ColumnMajorTileInterleave<64, 4>, +8 bias and the nibble interleave.
+    The 32-bit words viewed as ``[N/4][K/64][4][8]`` = (n4, ktile, c, v) hold, in destination nibble d,
+    ``(q[perm(64*ktile + 8*v + e), 4*n4 + c] + 8) & 15`` with ``e = _REF_NIB4[d]``."""
+    K, N = q_kn.shape
+    if K % 64 or N % 64:
+        raise ValueError("reference int4 layout needs K % 64 == 0 and N % 64 == 0")
+    u = ((q_kn.to(torch.int16) + 8) & 0xF).to(torch.uint8)                    # [K, N] biased nibbles
+    kidx = torch.arange(K)
+    perm = 32 * (kidx // 32) + _REF_ROW_PERM4[kidx % 32]
+    a2 = u[perm].t().contiguous()                                            # [N, K]: A2[n, k'] = u[perm(k'), n]
+    t = a2.view(N // 4, 4, K // 64, 8, 8).permute(0, 2, 1, 3, 4)             # [n4, ktile, c, v, e]
+    t = t[..., _REF_NIB4].contiguous()                                       # [n4, ktile, c, v, d]
+    lo, hi = t[..., 0::2], t[..., 1::2]                                      # nibble 2b -> low half of byte b
+    return (lo | (hi << 4)).contiguous().view(torch.int8).view(K, N // 2)
+
+
+def ref_layout4_inv(w_ref: torch.Tensor) -> torch.Tensor:
+    """Inverse of :func:`ref_layout4`: reference int4 bytes ``[K, N/2]`` -> int8 values ``[K, N]`` in [-8, 7]."""
+    K, N2 = w_ref.shape
+    N = N2 * 2
+    b = w_ref.contiguous().view(torch.uint8).view(N // 4, K // 64, 4, 8, 4)
+    t = torch.stack([b & 0xF, b >> 4], dim=-1).reshape(N // 4, K // 64, 4, 8, 8)   # [n4, ktile, c, v, d]
+    t = t[..., torch.argsort(_REF_NIB4)]                                          # [.., e]
+    a2 = t.permute(0, 2, 1, 3, 4).contiguous().view(N, K)                          # A2[n, k']
+    kidx = torch.arange(K)
+    perm = 32 * (kidx // 32) + _REF_ROW_PERM4[kidx % 32]
+    u = torch.empty(K, N, dtype=torch.uint8)
+    u[perm] = a2.t()
+    return (u.to(torch.int16) - 8).to(torch.int8).contiguous()
+
+
+def b200_layout4(q_kn: torch.Tensor) -> torch.Tensor:
+    """int4 values ``[K, N]`` -> the b200 int4 layout, shaped ``[K, N/2]`` int8 like the reference's
+    processed tensor: output-feature-major rows of K/2 bytes; in every 32-bit word (8 consecutive k) nibble p < 4 holds
+    ``q[8j + 2p] + 8`` and nibble 4 + p holds ``q[8j + 2p + 1] + 8`` -- ``(word >> 4p) & 0x000f000f`` is the adjacent-k pair."""
+    K, N = q_kn.shape
+    u = ((q_kn.t().contiguous().to(torch.int16) + 8) & 0xF).to(torch.uint8).view(N, K // 8, 8)   # [n, word, k%8]
+    t = u[..., _REF_NIB4]                                                                         # nibble d <- k offset
+    return (t[..., 0::2] | (t[..., 1::2] << 4)).contiguous().view(torch.int8).view(K, N // 2)
+
+
+def b200_layout4_inv(w4: torch.Tensor) -> torch.Tensor:
+    K, N2 = w4.shape
+    N = N2 * 2
+    b = w4.contiguous().view(torch.uint8).view(N, K // 8, 4)
+    t = torch.stack([b & 0xF, b >> 4], dim=-1).reshape(N, K // 8, 8)
+    u = t[..., torch.argsort(_REF_NIB4)].reshape(N, K)
+    return (u.to(torch.int16) - 8).to(torch.int8).t().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
 # K1 GEMM arithmetic (the parity target) and the north-star CPU baseline
 # ------------------------------------------------------------------------------------------------
 def dequantize(q_kn: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
@@ -212,8 +308,9 @@ def ref_lib() -> Optional[ctypes.CDLL]:
         if not os.path.exists(p):
             return None
         _ref_lib = ctypes.CDLL(p)
-        for f in ("ref_quant_fp16", "ref_quant_fp32", "ref_preprocess"):
-            getattr(_ref_lib, f).restype = ctypes.c_int
+        for f in ("ref_quant_fp16", "ref_quant_fp32", "ref_preprocess", "ref_quant4_fp16", "ref_quant4_fp32", "ref_preprocess4"):
+            if hasattr(_ref_lib, f):
+                getattr(_ref_lib, f).restype = ctypes.c_int
     return _ref_lib
 
 
@@ -253,6 +350,34 @@ def ref_preprocess(q_kn: torch.Tensor) -> torch.Tensor:
     q_kn = q_kn.contiguous()
     out = torch.empty(K, N, dtype=torch.int8)
     rc = lib.ref_preprocess(_ptr(out), _ptr(q_kn), ctypes.c_size_t(K), ctypes.c_size_t(N))
+    assert rc == 0, "reference preprocessor threw"
+    return out
+
+
+def ref_quantize4(w_kn: torch.Tensor):
+    """Run the REFERENCE ``symmetric_quantize`` with PACKED_INT4_WEIGHT_ONLY. Returns (unprocessed packed [K,N/2],
+    processed [K,N/2], scales)."""
+    lib = ref_lib()
+    assert lib is not None and hasattr(lib, "ref_quant4_fp16"), "oracle/_ref/libref_oracle.so not built (make -C oracle ref)"
+    K, N = w_kn.shape
+    w_kn = w_kn.contiguous()
+    unp = torch.empty(K, N // 2, dtype=torch.int8)
+    pro = torch.empty(K, N // 2, dtype=torch.int8)
+    sc = torch.empty(N, dtype=w_kn.dtype)
+    fn = lib.ref_quant4_fp16 if w_kn.dtype == torch.float16 else lib.ref_quant4_fp32
+    rc = fn(_ptr(pro), _ptr(unp), _ptr(sc), _ptr(w_kn), ctypes.c_size_t(K), ctypes.c_size_t(N))
+    assert rc == 0, "reference quantiser threw"
+    return unp, pro, sc
+
+
+def ref_preprocess4(p_kn2: torch.Tensor) -> torch.Tensor:
+    """Run the REFERENCE ``preprocess_weights(is_int4=True)`` (arch 80) on packed int4 ``[K, N/2]`` (K x N elements)."""
+    lib = ref_lib()
+    assert lib is not None and hasattr(lib, "ref_preprocess4"), "oracle/_ref/libref_oracle.so not built (make -C oracle ref)"
+    K, N2 = p_kn2.shape
+    p_kn2 = p_kn2.contiguous()
+    out = torch.empty(K, N2, dtype=torch.int8)
+    rc = lib.ref_preprocess4(_ptr(out), _ptr(p_kn2), ctypes.c_size_t(K), ctypes.c_size_t(2 * N2))
     assert rc == 0, "reference preprocessor threw"
     return out
 
