@@ -173,12 +173,22 @@ size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K)
 }
 
 namespace {
-// EETQ_B200_GEMV_MMA=0 sends M = 2..8 back to the SIMT kernel (A/B measurements)
-bool gemv_mma_on()
+// EETQ_B200_GEMV_MMA (A/B measurements): 0 sends M = 2..8 back to the SIMT kernel, 1 = token-major mma.sync kernel,
+// 2 = weights-in-A mma.sync kernel
+int gemv_mma_mode()
 {
-    static const bool v = [] {
+    static const int v = [] {
         const char* e = getenv("EETQ_B200_GEMV_MMA");
-        return !(e != nullptr && e[0] == '0');
+        return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    }();
+    return v;
+}
+// EETQ_B200_GEMV4_MMA: 1 sends int4 decode rows to the weights-in-A mma.sync kernel instead of the SIMT kernel
+int gemv4_mma_mode()
+{
+    static const int v = [] {
+        const char* e = getenv("EETQ_B200_GEMV4_MMA");
+        return (e != nullptr && e[0] >= '0' && e[0] <= '1') ? e[0] - '0' : 0;
     }();
     return v;
 }
@@ -189,8 +199,10 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
 {
     if (int rc = check_forward_args("w8a16_gemm", x, ldx, w_b200, scales, y, ldy, M, N, K, dtype))
         return rc;
-    EB_CHECK_ARG(!((flags & EETQ_B200_FLAG_FORCE_GEMV) && (flags & EETQ_B200_FLAG_FORCE_TC)),
-                 "w8a16_gemm: FORCE_GEMV and FORCE_TC are exclusive");
+    {
+        const int forced = flags & (EETQ_B200_FLAG_FORCE_GEMV | EETQ_B200_FLAG_FORCE_TC | EETQ_B200_FLAG_FORCE_MMA2);
+        EB_CHECK_ARG((forced & (forced - 1)) == 0, "w8a16_gemm: the FORCE_* flags are exclusive");
+    }
     EB_CHECK_ARG(residual == nullptr || (ldr >= N && (ldr % 8) == 0 && aligned16(residual)), "w8a16_gemm: bad residual stride/alignment");
     if (M == 0)
         return EETQ_B200_OK;  // empty batch: nothing to enqueue
@@ -213,7 +225,13 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
         use_gemv = false;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (use_gemv && M >= 3 && gemv_mma_on() && gemv_mma_supported(int(M), K))  // M = 2: the SIMT kernel measured faster
+    if (flags & EETQ_B200_FLAG_FORCE_MMA2) {
+        EB_CHECK_ARG(trace == nullptr && gemv_mma2_supported(int(M < 9 ? M : 9), K, 8), "w8a16_gemm: FORCE_MMA2 needs M <= 8 (and K that fits)");
+        return launch_gemv_mma2(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, 8, pdl, s);
+    }
+    if (use_gemv && M >= 3 && gemv_mma_mode() == 2 && gemv_mma2_supported(int(M), K, 8))
+        return launch_gemv_mma2(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, 8, pdl, s);
+    if (use_gemv && M >= 3 && gemv_mma_mode() >= 1 && gemv_mma_supported(int(M), K))  // M = 2: the SIMT kernel measured faster
         return launch_gemv_mma(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, pdl, s);
     if (use_gemv) {
         GemvExtras ex;
@@ -393,13 +411,22 @@ int eetq_b200_w4a16_gemm(const void* x, int64_t ldx, const uint8_t* q4_b200, con
 {
     if (int rc = check_forward_args("w4a16_gemm", x, ldx, q4_b200, scales, y, ldy, M, N, K, dtype))
         return rc;
-    EB_CHECK_ARG(!(flags & (EETQ_B200_FLAG_FORCE_GEMV | EETQ_B200_FLAG_FORCE_TC)), "w4a16_gemm: FORCE_* flags are not supported");
+    EB_CHECK_ARG(!(flags & EETQ_B200_FLAG_FORCE_TC), "w4a16_gemm: FORCE_TC is not supported");
+    EB_CHECK_ARG(!((flags & EETQ_B200_FLAG_FORCE_GEMV) && (flags & EETQ_B200_FLAG_FORCE_MMA2)), "w4a16_gemm: the FORCE_* flags are exclusive");
     if (M == 0)
         return EETQ_B200_OK;
     if (int rc = check_arch())
         return rc;
     const bool pdl = (flags & EETQ_B200_FLAG_PDL) != 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (flags & EETQ_B200_FLAG_FORCE_MMA2) {
+        EB_CHECK_ARG(gemv_mma2_supported(int(M < 9 ? M : 9), K, 4), "w4a16_gemm: FORCE_MMA2 needs M <= 8 and K %% 128 == 0");
+        return launch_gemv_mma2(x, ldx, reinterpret_cast<const int8_t*>(q4_b200), scales, bias, nullptr, 0, y, ldy, int(M), N, K, dtype, 4, pdl, s);
+    }
+    if (flags & EETQ_B200_FLAG_FORCE_GEMV)
+        EB_CHECK_ARG(M <= EETQ_B200_GEMV4_MAX_M, "w4a16_gemm: FORCE_GEMV needs M <= %d", EETQ_B200_GEMV4_MAX_M);
+    if (M <= EETQ_B200_GEMV4_MAX_M && !(flags & EETQ_B200_FLAG_FORCE_GEMV) && gemv4_mma_mode() == 1 && gemv_mma2_supported(int(M), K, 4))
+        return launch_gemv_mma2(x, ldx, reinterpret_cast<const int8_t*>(q4_b200), scales, bias, nullptr, 0, y, ldy, int(M), N, K, dtype, 4, pdl, s);
     if (M <= EETQ_B200_GEMV4_MAX_M) {
         GemvExtras ex;
         ex.wbits = 4;

@@ -148,6 +148,11 @@ int check_forward_args(const char* who, const void* x, int64_t ldx, const void* 
 bool gemv_mma_supported(int M, int64_t K);
 int launch_gemv_mma(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
                     int64_t ldr, void* y, int64_t ldy, int M, int64_t N, int64_t K, int dtype, bool pdl, cudaStream_t stream);
+// v2 of the same (weights in the MMA's A role: half the instructions per weight; int8 and int4 weights, 1 <= M <= 8)
+bool gemv_mma2_supported(int M, int64_t K, int wbits);
+int launch_gemv_mma2(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
+                     int64_t ldr, void* y, int64_t ldy, int M, int64_t N, int64_t K, int dtype, int wbits, bool pdl,
+                     cudaStream_t stream);
 
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,

@@ -262,7 +262,8 @@ def w8_a16_gemm_residual(input: torch.Tensor, weight: torch.Tensor, scale: torch
     return out
 
 
-def w4_a16_gemm(input: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+def w4_a16_gemm(input: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                flags: int = _cabi.FLAG_DEFAULT) -> torch.Tensor:
     """``y = input @ dequant(weight)`` for packed-int4 weights in the b200 int4 layout (``[K, N/2]`` int8 from
     ``quant_weights(w, torch.quint4x2)`` / ``preprocess_weights(w, is_int4=True)``).  Same arithmetic as ``w8_a16_gemm`` with q in
     [-8, 7]; what the reference's compiled-but-unselectable Int4b kernels compute (weightOnlyBatchedGemv/kernel.h:68-116)."""
@@ -289,7 +290,7 @@ def w4_a16_gemm(input: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, 
             L = _cabi.lib()
             ws = _workspace(input.device, int(L.eetq_b200_w4a16_workspace_bytes(M, N, K)))
             rc = L.eetq_b200_w4a16_gemm(_vp(x2), x2.stride(0) if M > 1 else K, _vp(weight), _vp(scale), _vp(bias), _vp(out), N, M, N, K,
-                                        _DTYPE_CODE[input.dtype], _vp(ws), 0 if ws is None else ws.numel(), _cabi.FLAG_DEFAULT, _stream())
+                                        _DTYPE_CODE[input.dtype], _vp(ws), 0 if ws is None else ws.numel(), flags, _stream())
             _cabi.check(rc, "eetq_b200_w4a16_gemm")
     return out
 

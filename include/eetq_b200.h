@@ -57,7 +57,8 @@ enum {
     EETQ_B200_FLAG_DEFAULT    = 0,
     EETQ_B200_FLAG_FORCE_GEMV = 1, /* force the SIMT streaming kernel (M <= EETQ_B200_GEMV_MAX_M) */
     EETQ_B200_FLAG_FORCE_TC   = 2, /* force the tcgen05 kernel */
-    EETQ_B200_FLAG_PDL        = 4  /* launch with programmatic-dependent-launch attribute */
+    EETQ_B200_FLAG_PDL        = 4, /* launch with programmatic-dependent-launch attribute */
+    EETQ_B200_FLAG_FORCE_MMA2 = 8  /* force the mma.sync streaming kernel with the weights in the A role (M <= 8) */
 };
 
 #define EETQ_B200_GEMV_MAX_M 8

@@ -130,8 +130,13 @@ def test_argument_validation_before_any_launch():
         eetq_b200.w8_a16_gemm(x, w, s)
     with pytest.raises(RuntimeError, match="int4 or int8"):
         eetq_b200.quant_weights(torch.zeros(64, 64, dtype=torch.float16), torch.int32, False)
-    with pytest.raises(NotImplementedError):
-        eetq_b200.preprocess_weights(w, is_int4=True)
+    if not torch.cuda.is_available():  # int4 is implemented; like every op it needs the device (no CPU path)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            eetq_b200.preprocess_weights(w, is_int4=True)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            eetq_b200.quant_weights(torch.zeros(64, 64, dtype=torch.float16), torch.quint4x2, False)
+    with pytest.raises(RuntimeError, match="2-D int8"):
+        eetq_b200.w4_a16_gemm(x.half(), w.float(), s)
 
 
 def test_eet_quantize_int8_ingest_uses_scb_scales(monkeypatch):

@@ -174,3 +174,19 @@ def test_w4a16_against_live_reference_gemv(cuda, oracle, K, N, M):
     assert e_ours <= 1e-3
     assert oracle.norm_rel_err(y.cpu(), y_ref.cpu()) <= 5e-3, (e_ours, e_ref)   # reference's fp16 accumulation dominates
     assert e_ours <= e_ref + 1e-4
+
+
+@pytest.mark.parametrize("K,N", LLAMA7B + [(128, 64), (8192, 1024), (1024, 1728)])
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8])
+def test_w4a16_mma_stream_kernel_matches_oracle(cuda, oracle, K, N, M):
+    """The mma.sync streaming kernel with the weights in the A role, int4 nibbles (gemv_mma.cu v2), forced through the flag."""
+    from eetq_b200 import _cabi
+    q, s, wq, sd = make4(oracle, cuda, K, N)
+    x = oracle.synth_act(M, K)
+    y = eetq_b200.w4_a16_gemm(x.to(cuda), wq, sd, flags=_cabi.FLAG_FORCE_MMA2)
+    assert oracle.norm_rel_err(y.cpu(), ref_out(oracle, x, q, s)) <= TOL[torch.float16]
+    if (K, N) == (1024, 1728):
+        xb = oracle.synth_act(M, K, dtype=torch.bfloat16)
+        bias = (torch.randn(N) * 0.1).to(torch.bfloat16)
+        yb = eetq_b200.w4_a16_gemm(xb.to(cuda), wq, sd.to(torch.bfloat16), bias.to(cuda), flags=_cabi.FLAG_FORCE_MMA2)
+        assert oracle.norm_rel_err(yb.cpu(), ref_out(oracle, xb, q, s.to(torch.bfloat16), bias)) <= TOL[torch.bfloat16]
