@@ -15,9 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EETQ_B200_LIB") or os.path.join(_HERE, "libeetq_b200.so")
 
 F16, BF16, F32 = 0, 1, 2
-FLAG_DEFAULT, FLAG_FORCE_GEMV, FLAG_FORCE_TC, FLAG_PDL, FLAG_FORCE_MMA2 = 0, 1, 2, 4, 8
+FLAG_DEFAULT, FLAG_FORCE_GEMV, FLAG_FORCE_TC, FLAG_PDL, FLAG_FORCE_MMA = 0, 1, 2, 4, 8
 GEMV_MAX_M = 8
-GEMV4_MAX_M = 4
+GEMV4_MAX_M = 8
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -173,22 +173,12 @@ size_t eetq_b200_workspace_bytes(int64_t M, int64_t N, int64_t K)
 }
 
 namespace {
-// EETQ_B200_GEMV_MMA (A/B measurements): 0 sends M = 2..8 back to the SIMT kernel, 1 = token-major mma.sync kernel,
-// 2 = weights-in-A mma.sync kernel
-int gemv_mma_mode()
+// EETQ_B200_GEMV_MMA=0 (A/B measurements) keeps 3..8 rows on the SIMT kernel instead of the mma.sync streaming kernel
+bool gemv_mma_on()
 {
-    static const int v = [] {
+    static const bool v = [] {
         const char* e = getenv("EETQ_B200_GEMV_MMA");
-        return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
-    }();
-    return v;
-}
-// EETQ_B200_GEMV4_MMA: 1 sends int4 decode rows to the weights-in-A mma.sync kernel instead of the SIMT kernel
-int gemv4_mma_mode()
-{
-    static const int v = [] {
-        const char* e = getenv("EETQ_B200_GEMV4_MMA");
-        return (e != nullptr && e[0] >= '0' && e[0] <= '1') ? e[0] - '0' : 0;
+        return !(e != nullptr && e[0] == '0');
     }();
     return v;
 }
@@ -200,7 +190,7 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
     if (int rc = check_forward_args("w8a16_gemm", x, ldx, w_b200, scales, y, ldy, M, N, K, dtype))
         return rc;
     {
-        const int forced = flags & (EETQ_B200_FLAG_FORCE_GEMV | EETQ_B200_FLAG_FORCE_TC | EETQ_B200_FLAG_FORCE_MMA2);
+        const int forced = flags & (EETQ_B200_FLAG_FORCE_GEMV | EETQ_B200_FLAG_FORCE_TC | EETQ_B200_FLAG_FORCE_MMA);
         EB_CHECK_ARG((forced & (forced - 1)) == 0, "w8a16_gemm: the FORCE_* flags are exclusive");
     }
     EB_CHECK_ARG(residual == nullptr || (ldr >= N && (ldr % 8) == 0 && aligned16(residual)), "w8a16_gemm: bad residual stride/alignment");
@@ -225,14 +215,14 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
         use_gemv = false;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (flags & EETQ_B200_FLAG_FORCE_MMA2) {
-        EB_CHECK_ARG(trace == nullptr && gemv_mma2_supported(int(M < 9 ? M : 9), K, 8), "w8a16_gemm: FORCE_MMA2 needs M <= 8 (and K that fits)");
-        return launch_gemv_mma2(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, 8, pdl, s);
+    if (flags & EETQ_B200_FLAG_FORCE_MMA) {
+        EB_CHECK_ARG(trace == nullptr && gemv_mma_supported(int(M < 9 ? M : 9), K, 8), "w8a16_gemm: FORCE_MMA needs M <= 8 (and K that fits)");
+        return launch_gemv_mma(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, 8, pdl, s);
     }
-    if (use_gemv && M >= 3 && gemv_mma_mode() == 2 && gemv_mma2_supported(int(M), K, 8))
-        return launch_gemv_mma2(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, 8, pdl, s);
-    if (use_gemv && M >= 3 && gemv_mma_mode() >= 1 && gemv_mma_supported(int(M), K))  // M = 2: the SIMT kernel measured faster
-        return launch_gemv_mma(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, pdl, s);
+    // 3..8 rows: the mma.sync streaming kernel (M-independent instruction count); 1 and 2 rows: the SIMT kernel measured faster
+    // (profiles/r02_kbench_mma2.json: 4096x4096 M = 3 / 4: 8.1 / 8.2 us vs 8.7 / 8.9 SIMT)
+    if (use_gemv && M >= 3 && gemv_mma_on() && gemv_mma_supported(int(M), K, 8))
+        return launch_gemv_mma(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, 8, pdl, s);
     if (use_gemv) {
         GemvExtras ex;
         ex.residual = residual;
@@ -400,8 +390,10 @@ size_t w4_tc_scratch_bytes(int64_t M, int64_t N, int64_t K) { return (gemm_tc_wo
 
 size_t eetq_b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K)
 {
-    if (M <= EETQ_B200_GEMV4_MAX_M || N <= 0 || K <= 0)
+    if (M <= EETQ_B200_GEMV4_SIMT_MAX_M || N <= 0 || K <= 0)
         return 0;
+    if (M <= EETQ_B200_GEMV4_MAX_M && gemv_mma_on() && gemv_mma_supported(int(M), K, 4))
+        return 0;  // streamed by the mma.sync kernel, nothing is widened
     return w4_tc_scratch_bytes(M, N, K) + size_t(N) * size_t(K);
 }
 
@@ -412,29 +404,32 @@ int eetq_b200_w4a16_gemm(const void* x, int64_t ldx, const uint8_t* q4_b200, con
     if (int rc = check_forward_args("w4a16_gemm", x, ldx, q4_b200, scales, y, ldy, M, N, K, dtype))
         return rc;
     EB_CHECK_ARG(!(flags & EETQ_B200_FLAG_FORCE_TC), "w4a16_gemm: FORCE_TC is not supported");
-    EB_CHECK_ARG(!((flags & EETQ_B200_FLAG_FORCE_GEMV) && (flags & EETQ_B200_FLAG_FORCE_MMA2)), "w4a16_gemm: the FORCE_* flags are exclusive");
+    EB_CHECK_ARG(!((flags & EETQ_B200_FLAG_FORCE_GEMV) && (flags & EETQ_B200_FLAG_FORCE_MMA)), "w4a16_gemm: the FORCE_* flags are exclusive");
     if (M == 0)
         return EETQ_B200_OK;
     if (int rc = check_arch())
         return rc;
-    const bool pdl = (flags & EETQ_B200_FLAG_PDL) != 0;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (flags & EETQ_B200_FLAG_FORCE_MMA2) {
-        EB_CHECK_ARG(gemv_mma2_supported(int(M < 9 ? M : 9), K, 4), "w4a16_gemm: FORCE_MMA2 needs M <= 8 and K %% 128 == 0");
-        return launch_gemv_mma2(x, ldx, reinterpret_cast<const int8_t*>(q4_b200), scales, bias, nullptr, 0, y, ldy, int(M), N, K, dtype, 4, pdl, s);
+    const bool pdl     = (flags & EETQ_B200_FLAG_PDL) != 0;
+    cudaStream_t s     = static_cast<cudaStream_t>(stream);
+    const int8_t* w4   = reinterpret_cast<const int8_t*>(q4_b200);
+    if (flags & EETQ_B200_FLAG_FORCE_MMA) {
+        EB_CHECK_ARG(gemv_mma_supported(int(M < 9 ? M : 9), K, 4), "w4a16_gemm: FORCE_MMA needs M <= 8 and K %% 128 == 0");
+        return launch_gemv_mma(x, ldx, w4, scales, bias, nullptr, 0, y, ldy, int(M), N, K, dtype, 4, pdl, s);
     }
     if (flags & EETQ_B200_FLAG_FORCE_GEMV)
-        EB_CHECK_ARG(M <= EETQ_B200_GEMV4_MAX_M, "w4a16_gemm: FORCE_GEMV needs M <= %d", EETQ_B200_GEMV4_MAX_M);
-    if (M <= EETQ_B200_GEMV4_MAX_M && !(flags & EETQ_B200_FLAG_FORCE_GEMV) && gemv4_mma_mode() == 1 && gemv_mma2_supported(int(M), K, 4))
-        return launch_gemv_mma2(x, ldx, reinterpret_cast<const int8_t*>(q4_b200), scales, bias, nullptr, 0, y, ldy, int(M), N, K, dtype, 4, pdl, s);
-    if (M <= EETQ_B200_GEMV4_MAX_M) {
+        EB_CHECK_ARG(M <= EETQ_B200_GEMV4_SIMT_MAX_M, "w4a16_gemm: FORCE_GEMV needs M <= %d", EETQ_B200_GEMV4_SIMT_MAX_M);
+    // measured (profiles/r02_kbench_mma2.json): one row streams fastest through the SIMT kernel (4096x4096: 5.4 vs 7.0 us); from two
+    // rows on the mma.sync kernel wins, by up to 1.7x at K = 11008 / 4 rows, and it also beats widening + tcgen05 up to 8 rows
+    if (M >= 2 && M <= EETQ_B200_GEMV4_MAX_M && !(flags & EETQ_B200_FLAG_FORCE_GEMV) && gemv_mma_on() && gemv_mma_supported(int(M), K, 4))
+        return launch_gemv_mma(x, ldx, w4, scales, bias, nullptr, 0, y, ldy, int(M), N, K, dtype, 4, pdl, s);
+    if (M <= EETQ_B200_GEMV4_SIMT_MAX_M) {
         GemvExtras ex;
         ex.wbits = 4;
-        return launch_gemv(x, ldx, reinterpret_cast<const int8_t*>(q4_b200), scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl, s);
+        return launch_gemv(x, ldx, w4, scales, bias, y, ldy, int(M), N, K, dtype, ex, pdl, s);
     }
     const size_t scratch = w4_tc_scratch_bytes(M, N, K);
     if (workspace == nullptr || !aligned16(workspace) || workspace_bytes < scratch + size_t(N) * size_t(K)) {
-        set_error("w4a16_gemm: M > %d needs a workspace of %zu bytes (got %zu)", EETQ_B200_GEMV4_MAX_M, scratch + size_t(N) * size_t(K),
+        set_error("w4a16_gemm: M = %lld needs a workspace of %zu bytes (got %zu)", (long long)M, scratch + size_t(N) * size_t(K),
                   workspace_bytes);
         return EETQ_B200_EWORKSPACE;
     }

@@ -144,15 +144,11 @@ int check_arch();
 int check_forward_args(const char* who, const void* x, int64_t ldx, const void* w, const void* scales, const void* y, int64_t ldy,
                        int64_t M, int64_t N, int64_t K, int dtype, int64_t n_out = -1);
 
-// tensor-core (mma.sync) streaming kernel for 2 <= M <= 8 decode rows (gemv_mma.cu)
-bool gemv_mma_supported(int M, int64_t K);
+// tensor-core (mma.sync) streaming kernel for up to 8 decode rows, weights in the MMA's A role, int8 or int4 weights (gemv_mma.cu)
+bool gemv_mma_supported(int M, int64_t K, int wbits);
 int launch_gemv_mma(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
-                    int64_t ldr, void* y, int64_t ldy, int M, int64_t N, int64_t K, int dtype, bool pdl, cudaStream_t stream);
-// v2 of the same (weights in the MMA's A role: half the instructions per weight; int8 and int4 weights, 1 <= M <= 8)
-bool gemv_mma2_supported(int M, int64_t K, int wbits);
-int launch_gemv_mma2(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
-                     int64_t ldr, void* y, int64_t ldy, int M, int64_t N, int64_t K, int dtype, int wbits, bool pdl,
-                     cudaStream_t stream);
+                    int64_t ldr, void* y, int64_t ldy, int M, int64_t N, int64_t K, int dtype, int wbits, bool pdl,
+                    cudaStream_t stream);
 
 size_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemm_tc(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,

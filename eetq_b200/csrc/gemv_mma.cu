@@ -1,24 +1,15 @@
-// gemv_mma.cu -- decode-time w8a16 streaming kernel for 2 <= M <= 8 token rows (sm_100a).
+// gemv_mma.cu -- decode-time streaming kernel for 2..8 token rows, int8 or int4 weights (sm_100a).
 //
 // Replaces, for the batched-decode rows, the reference's weight_only_batched_gemv<..., BatchSize 2..4>
-//   /root/reference/csrc/weightOnlyBatchedGemv/kernel.h:294-468 (dispatch kernelLauncher.cu:165-199)
+//   /root/reference/csrc/weightOnlyBatchedGemv/kernel.h:294-468 (dispatch kernelLauncher.cu:165-199; Int4b details :68-116)
 // whose cost grows with the batch (one HFMA2 chain per row per weight pair, fp16 accumulation).  Here the weight stream is
 // the same register-fed LDG.128 stream as the M = 1 kernel (gemv.cu), but the arithmetic goes through warp-level
-// mma.sync.m16n8k16 with the roles swapped -- D[token, feature] += X[token, k] * W[k, feature] -- so the instruction
-// count per weight byte is independent of M (8 PRMT + 4 LDS.64 + 4 MMA per 16 weights per thread) and accumulation is fp32:
+// mma.sync.m16n8k16 with the WEIGHTS in the A role -- D[feature (16), token (8)] += W[feature, k] * X[k, token] -- so the
+// instruction count per weight byte is independent of M and accumulation is fp32 (design notes at the kernel).
+// A first version with the tokens in the 16-row role (4 MMAs per 16 weights per lane, 8-row tiles) was measured slower on every
+// cell it served (profiles/r02_kbench_mma2.json) and removed.
 //
-//   * b200 layout: row n of the weight = the K biased bytes u = q + 128 of feature n.  Lane (g = lane/4, t = lane%4) of a
-//     warp loads 16 bytes of row (tile_row0 + g) at k offset 16 t of a 64-k block: exactly the B fragment (k x n, "col")
-//     of FOUR m16n8k16 MMAs under a fixed permutation of k that the activation fragment mirrors (sums over k do not care);
-//   * PRMT puts each byte under the fp16 exponent byte 0x64 -> fp16(1024 + u), consumed by the MMA as is; the constant
-//     (1024 + 128) * sum_k x[m,k] is removed once per output in the epilogue (bf16: bytes -> exact bf16(q), no offset);
-//   * activations (M x K, a few KB) are staged once per CTA in shared memory with an 8-byte row pad, so the A fragments are
-//     conflict-free LDS.64; token rows >= M are zero;
-//   * the 8 warps of a CTA split K into contiguous ranges and keep 16 x 16-byte weight loads in flight per thread
-//     (two register buffers of 8), the first two buffers issued BEFORE griddepcontrol.wait; per-warp partial tiles are
-//     summed through shared memory; scale, bias and the optional residual are applied in the epilogue.
-//
-// Algorithmic bytes per call: K*N + 2*N + 2*M*K + 2*M*N; each weight byte is read exactly once.
+// Algorithmic bytes per call: K*N*bits/8 + 2*N + 2*M*K + 2*M*N; each weight byte is read exactly once.
 #include "common.cuh"
 
 namespace eetq_b200 {
@@ -42,7 +33,7 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
                      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// one 32-bit word of 4 biased bytes -> the two B-fragment registers (k pairs {0,1} and {2,3})
+// one 32-bit word of 4 biased bytes -> two operand registers (k pairs {0,1} and {2,3})
 template <typename T>
 __device__ __forceinline__ void cvt_word(uint32_t w, uint32_t& b0, uint32_t& b1)
 {
@@ -60,245 +51,9 @@ __device__ __forceinline__ void cvt_word(uint32_t w, uint32_t& b0, uint32_t& b1)
     }
 }
 
-template <typename T>
-struct MmaOffset {
-    static constexpr float value = DTypeOf<T>::value == EETQ_B200_F16 ? 1152.f : 0.f;
-};
-
-// dynamic smem: [MP rows of (K + 4) T] | [kWarps][tiles][MP][8] fp32 partials | [MP] fp32 row sums
-template <typename T, int MP>
-__global__ void __launch_bounds__(kThreads, 2)
-    w8a16_gemv_mma_kernel(const T* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ w, const T* __restrict__ scales,
-                          const T* __restrict__ bias, const T* __restrict__ residual, int64_t ldr, T* __restrict__ y, int64_t ldy,
-                          int M, int N, int K, int max_tiles)
-{
-    extern __shared__ __align__(16) uint8_t mma_smem[];
-    const int xstride = 2 * K + 8;  // bytes per staged activation row (8-byte pad: conflict-free LDS.64 fragments)
-    uint8_t* xs       = mma_smem;
-    float* partial    = reinterpret_cast<float*>(mma_smem + ((MP * xstride + 15) & ~15));
-    float* xsum       = partial + kWarps * max_tiles * MP * 8;
-
-    const int tid  = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int g    = lane >> 2;  // B fragment: feature inside the 8-row tile; A fragment: token row
-    const int t    = lane & 3;
-
-    const int row_begin = int((int64_t(blockIdx.x) * N) / gridDim.x);
-    const int row_end   = int((int64_t(blockIdx.x + 1) * N) / gridDim.x);
-    const int nrows     = row_end - row_begin;
-    const int ntiles    = (nrows + 7) >> 3;
-
-    // this warp's contiguous range of 64-k blocks
-    const int nkb_total = K >> 6;
-    const int kb0       = (warp * nkb_total) / kWarps;
-    const int nkb       = ((warp + 1) * nkb_total) / kWarps - kb0;
-    const int total     = ntiles * nkb;  // work items (tile, k-block) of this warp, tile-major
-
-    pdl_launch_dependents();
-
-    uint4 wb[2][kBuf];
-    // loader state: next item to fetch
-    int l_tile = 0, l_j = 0;
-    auto load_buf = [&](uint4 (&buf)[kBuf]) {
-#pragma unroll
-        for (int i = 0; i < kBuf; ++i) {
-            const int row = row_begin + l_tile * 8 + g;
-            if (l_tile < ntiles && row < row_end)
-                buf[i] = ldg_stream_128(w + int64_t(row) * K + int64_t(kb0 + l_j) * 64 + t * 16);
-            else
-                buf[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (++l_j == nkb) {
-                l_j = 0;
-                ++l_tile;
-            }
-        }
-    };
-    // weights do not depend on the previous kernel: start streaming before the dependency wait
-    if (nkb > 0) {
-        load_buf(wb[0]);
-        load_buf(wb[1]);
-    }
-    pdl_wait_prior_grids();
-
-    // stage the activations (rows >= M are zero) and their per-row sums
-    {
-        const int chunks_per_row = K >> 2;  // 8-byte pieces
-        float s[MP];
-#pragma unroll
-        for (int m = 0; m < MP; ++m)
-            s[m] = 0.f;
-#pragma unroll
-        for (int m = 0; m < MP; ++m) {
-            for (int c = tid; c < chunks_per_row; c += kThreads) {
-                uint2 v = make_uint2(0u, 0u);
-                if (m < M)
-                    v = *reinterpret_cast<const uint2*>(x + int64_t(m) * ldx + int64_t(c) * 4);
-                *reinterpret_cast<uint2*>(xs + m * xstride + c * 8) = v;
-                if constexpr (DTypeOf<T>::value == EETQ_B200_F16) {
-                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-                    s[m] += (a.x + a.y) + (b.x + b.y);
-                }
-            }
-        }
-        if constexpr (DTypeOf<T>::value == EETQ_B200_F16) {
-            float* red = partial;  // reused before any partial is written
-#pragma unroll
-            for (int m = 0; m < MP; ++m) {
-                float v = s[m];
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1)
-                    v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0)
-                    red[m * kWarps + warp] = v;
-            }
-            __syncthreads();
-            if (tid < MP) {
-                float v = 0.f;
-#pragma unroll
-                for (int wi = 0; wi < kWarps; ++wi)
-                    v += red[tid * kWarps + wi];
-                xsum[tid] = v;
-            }
-        }
-        __syncthreads();
-    }
-
-    // consumer state
-    int c_tile = 0, c_j = 0;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    auto flush = [&](int tile) {
-        if (g < MP)
-            *reinterpret_cast<float2*>(partial + ((warp * max_tiles + tile) * MP + g) * 8 + 2 * t) = make_float2(acc[0], acc[1]);
-        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    };
-    auto compute_buf = [&](const uint4 (&buf)[kBuf], int count) {
-#pragma unroll
-        for (int i = 0; i < kBuf; ++i) {
-            if (i < count) {
-                const uint32_t words[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
-                const uint8_t* xrow     = xs + g * xstride + ((kb0 + c_j) * 64 + t * 16) * 2;
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    uint32_t a[4] = {0u, 0u, 0u, 0u};
-                    if (g < MP) {
-                        const uint2 xv = *reinterpret_cast<const uint2*>(xrow + jj * 8);
-                        a[0] = xv.x;  // (token g, k pair {0,1})
-                        a[2] = xv.y;  // (token g, k pair {2,3})
-                    }
-                    uint32_t b0, b1;
-                    cvt_word<T>(words[jj], b0, b1);
-                    mma_16816<T>(acc, a, b0, b1);
-                }
-                if (++c_j == nkb) {
-                    flush(c_tile);
-                    c_j = 0;
-                    ++c_tile;
-                }
-            }
-        }
-    };
-
-    for (int done = 0; done < total; done += 2 * kBuf) {
-        const int n0 = min(kBuf, total - done);
-        compute_buf(wb[0], n0);
-        if (done + 2 * kBuf < total)
-            load_buf(wb[0]);
-        const int n1 = min(kBuf, total - done - kBuf);
-        if (n1 > 0) {
-            compute_buf(wb[1], n1);
-            if (done + 3 * kBuf < total)
-                load_buf(wb[1]);
-        }
-    }
-    __syncthreads();
-
-    // epilogue: cross-warp sum, remove the (1024 + 128) * sum(x) constant, per-channel scale (+bias, +residual), store
-    for (int idx = tid; idx < nrows * M; idx += kThreads) {
-        const int r    = idx / M;
-        const int m    = idx - r * M;
-        const int tile = r >> 3, f = r & 7;
-        float s        = 0.f;
-        if (nkb_total >= kWarps) {
-#pragma unroll
-            for (int wi = 0; wi < kWarps; ++wi)
-                s += partial[((wi * max_tiles + tile) * MP + m) * 8 + f];
-        }
-        else {
-            for (int wi = 0; wi < kWarps; ++wi)  // warps without any k-block never wrote their slot
-                if (((wi + 1) * nkb_total) / kWarps > (wi * nkb_total) / kWarps)
-                    s += partial[((wi * max_tiles + tile) * MP + m) * 8 + f];
-        }
-        if constexpr (DTypeOf<T>::value == EETQ_B200_F16)
-            s -= MmaOffset<T>::value * xsum[m];
-        const int n = row_begin + r;
-        float out   = s * to_float(scales[n]);
-        if (bias != nullptr)
-            out += to_float(bias[n]);
-        T o = from_float<T>(out);
-        if (residual != nullptr)
-            o = from_float<T>(to_float(o) + to_float(residual[int64_t(m) * ldr + n]));
-        y[int64_t(m) * ldy + n] = o;
-    }
-}
-
-template <typename T, int MP>
-int launch_mma(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, const T* residual, int64_t ldr, T* y,
-               int64_t ldy, int M, int N, int K, bool pdl, cudaStream_t stream)
-{
-    const DeviceInfo& di = device_info();
-    if (!di.ok) {
-        set_error("gemv_mma: device query failed");
-        return EETQ_B200_ECUDA;
-    }
-    constexpr int kMaxRows = 96;
-    const size_t x_bytes   = (size_t(MP) * (2 * size_t(K) + 8) + 15) & ~size_t(15);
-    // two CTAs per SM while the staged activations leave room for it
-    int ctas_per_sm = (x_bytes + 16384 <= size_t(di.max_smem_optin) / 2 - 2048) ? 2 : 1;
-    int grid        = di.sm_count * ctas_per_sm;
-    while ((N + grid - 1) / grid > kMaxRows)
-        grid += di.sm_count;
-    if (grid > N / 8)
-        grid = N / 8 > 0 ? N / 8 : 1;
-    const int max_rows  = (N + grid - 1) / grid;
-    const int max_tiles = (max_rows + 7) / 8 + 1;
-    const size_t smem   = x_bytes + size_t(kWarps) * max_tiles * MP * 8 * sizeof(float) + MP * sizeof(float) + 64;
-    if (smem > size_t(di.max_smem_optin)) {
-        set_error("gemv_mma: %zu bytes of shared memory needed (M=%d, K=%d)", smem, M, K);
-        return EETQ_B200_EINVAL;
-    }
-    auto kernel = w8a16_gemv_mma_kernel<T, MP>;
-    static size_t attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && attr_set[dev] < smem) {
-        EB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(di.max_smem_optin)));
-        attr_set[dev] = size_t(di.max_smem_optin);
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim          = dim3(unsigned(grid));
-    cfg.blockDim         = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream           = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs                                          = attr;
-    cfg.numAttrs                                       = pdl ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, x, ldx, w, scales, bias, residual, ldr, y, ldy, M, N, K, max_tiles);
-    count_launch();
-    if (e != cudaSuccess) {
-        set_error("gemv_mma launch failed: %s", cudaGetErrorString(e));
-        return EETQ_B200_ECUDA;
-    }
-    return EETQ_B200_OK;
-}
-
 // =====================================================================================================================
-// v2: weights in the A role.  D[feature (16), token (8)] += W[feature, k] * X[k, token]: one m16n8k16 consumes 16 features x 16 k
-// = 8 weights per lane, twice what the token-major arrangement above gets out of an instruction, and it takes int4 nibbles as
-// well as int8 bytes (WB):
+// D[feature (16), token (8)] += W[feature, k] * X[k, token]: one m16n8k16 consumes 16 features x 16 k = 8 weights per lane; int8
+// bytes or int4 nibbles (WB):
 //   * a work item is (16-row tile, k-block); lane (g = lane/4, t = lane%4) loads 16 bytes of row g and 16 bytes of row g + 8 at
 //     byte offset 16 t of the block's 64 bytes (int8: 64 k per block, 16 k per lane; int4: 128 k per block, 32 k per lane);
 //   * every group of 4 consecutive k of a lane (one int8 word, half an int4 word) is one MMA: A = {row g pair 0, row g+8 pair 0,
@@ -311,7 +66,7 @@ int launch_mma(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
 // Accumulation is fp32 inside the tensor core.  Rows >= M of the token tile are zero (lanes g >= MP feed zero B fragments).
 // =====================================================================================================================
 template <typename T, int WB>
-struct Mma2Offset {
+struct MmaOffset {
     static constexpr float value = DTypeOf<T>::value == EETQ_B200_F16 ? (WB == 8 ? 1152.f : 1032.f) : 0.f;
 };
 
@@ -332,7 +87,7 @@ __device__ __forceinline__ uint32_t cvt_nib_pair(uint32_t w, int p)
 // dynamic smem: [MP rows of (K + 4) T] | [kWarps][tiles][16][MP] fp32 partials | [MP] fp32 row sums
 template <typename T, int MP, int WB>
 __global__ void __launch_bounds__(kThreads, 2)
-    w8a16_gemv_mma2_kernel(const T* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ w, const T* __restrict__ scales,
+    w8a16_gemv_mma_kernel(const T* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ w, const T* __restrict__ scales,
                            const T* __restrict__ bias, const T* __restrict__ residual, int64_t ldr, T* __restrict__ y, int64_t ldy,
                            int M, int N, int K, int max_tiles)
 {
@@ -508,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 2)
             if (((wi + 1) * nkb_total) / kWarps > (wi * nkb_total) / kWarps)
                 s += partial[((wi * max_tiles + tile) * 16 + f) * MP + m];
         if constexpr (DTypeOf<T>::value == EETQ_B200_F16)
-            s -= Mma2Offset<T, WB>::value * xsum[m];
+            s -= MmaOffset<T, WB>::value * xsum[m];
         const int n = row_begin + r;
         float out   = s * to_float(scales[n]);
         if (bias != nullptr)
@@ -521,30 +276,37 @@ __global__ void __launch_bounds__(kThreads, 2)
 }
 
 template <typename T, int MP, int WB>
-int launch_mma2(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, const T* residual, int64_t ldr, T* y,
+int launch_mma(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, const T* residual, int64_t ldr, T* y,
                 int64_t ldy, int M, int N, int K, bool pdl, cudaStream_t stream)
 {
     const DeviceInfo& di = device_info();
     if (!di.ok) {
-        set_error("gemv_mma2: device query failed");
+        set_error("gemv_mma: device query failed");
         return EETQ_B200_ECUDA;
     }
     constexpr int kMaxRows = 96;
     const size_t x_bytes   = (size_t(MP) * (2 * size_t(K) + 8) + 15) & ~size_t(15);
-    int ctas_per_sm = (x_bytes + 32768 <= size_t(di.max_smem_optin) / 2 - 2048) ? 2 : 1;
-    int grid        = di.sm_count * ctas_per_sm;
-    while ((N + grid - 1) / grid > kMaxRows)
-        grid += di.sm_count;
-    if (grid > N / 16)
-        grid = N / 16 > 0 ? N / 16 : 1;
-    const int max_rows  = (N + grid - 1) / grid;
-    const int max_tiles = (max_rows + 15) / 16 + 1;
-    const size_t smem   = x_bytes + size_t(kWarps) * max_tiles * 16 * MP * sizeof(float) + MP * sizeof(float) + 64;
+    // geometry for a given number of CTAs per SM; two per SM whenever two footprints (+1 KB reserved each) fit the SM's shared memory
+    int grid = 0, max_tiles = 0;
+    size_t smem = 0;
+    auto plan = [&](int ctas_per_sm) {
+        grid = di.sm_count * ctas_per_sm;
+        while ((N + grid - 1) / grid > kMaxRows)
+            grid += di.sm_count;
+        if (grid > N / 16)
+            grid = N / 16 > 0 ? N / 16 : 1;
+        const int max_rows = (N + grid - 1) / grid;
+        max_tiles          = (max_rows + 15) / 16 + 1;
+        smem               = x_bytes + size_t(kWarps) * max_tiles * 16 * MP * sizeof(float) + MP * sizeof(float) + 64;
+    };
+    plan(2);
+    if (2 * (smem + 1024) > size_t(di.max_smem_optin) + 1024)
+        plan(1);
     if (smem > size_t(di.max_smem_optin)) {
-        set_error("gemv_mma2: %zu bytes of shared memory needed (M=%d, K=%d)", smem, M, K);
+        set_error("gemv_mma: %zu bytes of shared memory needed (M=%d, K=%d)", smem, M, K);
         return EETQ_B200_EINVAL;
     }
-    auto kernel = w8a16_gemv_mma2_kernel<T, MP, WB>;
+    auto kernel = w8a16_gemv_mma_kernel<T, MP, WB>;
     static size_t attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -565,64 +327,30 @@ int launch_mma2(const T* x, int64_t ldx, const uint8_t* w, const T* scales, cons
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, x, ldx, w, scales, bias, residual, ldr, y, ldy, M, N, K, max_tiles);
     count_launch();
     if (e != cudaSuccess) {
-        set_error("gemv_mma2 launch failed: %s", cudaGetErrorString(e));
+        set_error("gemv_mma launch failed: %s", cudaGetErrorString(e));
         return EETQ_B200_ECUDA;
     }
     return EETQ_B200_OK;
 }
 
 template <typename T, int WB>
-int launch_mma2_mp(const void* x, int64_t ldx, const uint8_t* w, const void* scales, const void* bias, const void* residual, int64_t ldr,
+int launch_mma_mp(const void* x, int64_t ldx, const uint8_t* w, const void* scales, const void* bias, const void* residual, int64_t ldr,
                    void* y, int64_t ldy, int M, int N, int K, bool pdl, cudaStream_t stream)
 {
     if (M <= 2)  // two staged rows: the activations of K = 11008 still leave room for two CTAs per SM
-        return launch_mma2<T, 2, WB>(static_cast<const T*>(x), ldx, w, static_cast<const T*>(scales), static_cast<const T*>(bias),
+        return launch_mma<T, 2, WB>(static_cast<const T*>(x), ldx, w, static_cast<const T*>(scales), static_cast<const T*>(bias),
                                      static_cast<const T*>(residual), ldr, static_cast<T*>(y), ldy, M, N, K, pdl, stream);
     if (M <= 4)
-        return launch_mma2<T, 4, WB>(static_cast<const T*>(x), ldx, w, static_cast<const T*>(scales), static_cast<const T*>(bias),
+        return launch_mma<T, 4, WB>(static_cast<const T*>(x), ldx, w, static_cast<const T*>(scales), static_cast<const T*>(bias),
                                      static_cast<const T*>(residual), ldr, static_cast<T*>(y), ldy, M, N, K, pdl, stream);
-    return launch_mma2<T, 8, WB>(static_cast<const T*>(x), ldx, w, static_cast<const T*>(scales), static_cast<const T*>(bias),
+    return launch_mma<T, 8, WB>(static_cast<const T*>(x), ldx, w, static_cast<const T*>(scales), static_cast<const T*>(bias),
                                  static_cast<const T*>(residual), ldr, static_cast<T*>(y), ldy, M, N, K, pdl, stream);
 }
 
 }  // namespace
 
-// true when the MMA streaming kernel can take this call (the staged activations must fit in shared memory)
-bool gemv_mma_supported(int M, int64_t K)
-{
-    const DeviceInfo& di = device_info();
-    if (!di.ok || M < 2 || M > 8)
-        return false;
-    const size_t mp = M <= 4 ? 4 : 8;
-    return mp * (2 * size_t(K) + 8) + 32768 <= size_t(di.max_smem_optin);
-}
-
-int launch_gemv_mma(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
-                    int64_t ldr, void* y, int64_t ldy, int M, int64_t N, int64_t K, int dtype, bool pdl, cudaStream_t stream)
-{
-    const uint8_t* wu = reinterpret_cast<const uint8_t*>(w);
-    if (dtype == EETQ_B200_F16) {
-        using T = __half;
-        if (M <= 4)
-            return launch_mma<T, 4>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
-                                    static_cast<const T*>(residual), ldr, static_cast<T*>(y), ldy, M, int(N), int(K), pdl, stream);
-        return launch_mma<T, 8>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
-                                static_cast<const T*>(residual), ldr, static_cast<T*>(y), ldy, M, int(N), int(K), pdl, stream);
-    }
-    if (dtype == EETQ_B200_BF16) {
-        using T = __nv_bfloat16;
-        if (M <= 4)
-            return launch_mma<T, 4>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
-                                    static_cast<const T*>(residual), ldr, static_cast<T*>(y), ldy, M, int(N), int(K), pdl, stream);
-        return launch_mma<T, 8>(static_cast<const T*>(x), ldx, wu, static_cast<const T*>(scales), static_cast<const T*>(bias),
-                                static_cast<const T*>(residual), ldr, static_cast<T*>(y), ldy, M, int(N), int(K), pdl, stream);
-    }
-    set_error("gemv_mma: unsupported activation dtype %d", dtype);
-    return EETQ_B200_EINVAL;
-}
-
-// v2 (weights in the A role): 1 <= M <= 8, int8 or int4 weights; int4 needs K % 128 == 0
-bool gemv_mma2_supported(int M, int64_t K, int wbits)
+// 1 <= M <= 8, int8 or int4 weights (int4 needs K % 128 == 0); the staged activations must fit in shared memory
+bool gemv_mma_supported(int M, int64_t K, int wbits)
 {
     const DeviceInfo& di = device_info();
     if (!di.ok || M < 1 || M > 8 || (wbits != 8 && wbits != 4) || (wbits == 4 && (K % 128) != 0))
@@ -631,23 +359,23 @@ bool gemv_mma2_supported(int M, int64_t K, int wbits)
     return mp * (2 * size_t(K) + 8) + 49152 <= size_t(di.max_smem_optin);
 }
 
-int launch_gemv_mma2(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
+int launch_gemv_mma(const void* x, int64_t ldx, const int8_t* w, const void* scales, const void* bias, const void* residual,
                      int64_t ldr, void* y, int64_t ldy, int M, int64_t N, int64_t K, int dtype, int wbits, bool pdl,
                      cudaStream_t stream)
 {
     const uint8_t* wu = reinterpret_cast<const uint8_t*>(w);
-    if (!gemv_mma2_supported(M, K, wbits)) {
-        set_error("gemv_mma2: unsupported call (M=%d, K=%lld, %d-bit weights)", M, (long long)K, wbits);
+    if (!gemv_mma_supported(M, K, wbits)) {
+        set_error("gemv_mma: unsupported call (M=%d, K=%lld, %d-bit weights)", M, (long long)K, wbits);
         return EETQ_B200_EINVAL;
     }
     if (dtype == EETQ_B200_F16)
-        return wbits == 8 ? launch_mma2_mp<__half, 8>(x, ldx, wu, scales, bias, residual, ldr, y, ldy, M, int(N), int(K), pdl, stream)
-                          : launch_mma2_mp<__half, 4>(x, ldx, wu, scales, bias, residual, ldr, y, ldy, M, int(N), int(K), pdl, stream);
+        return wbits == 8 ? launch_mma_mp<__half, 8>(x, ldx, wu, scales, bias, residual, ldr, y, ldy, M, int(N), int(K), pdl, stream)
+                          : launch_mma_mp<__half, 4>(x, ldx, wu, scales, bias, residual, ldr, y, ldy, M, int(N), int(K), pdl, stream);
     if (dtype == EETQ_B200_BF16)
         return wbits == 8
-                   ? launch_mma2_mp<__nv_bfloat16, 8>(x, ldx, wu, scales, bias, residual, ldr, y, ldy, M, int(N), int(K), pdl, stream)
-                   : launch_mma2_mp<__nv_bfloat16, 4>(x, ldx, wu, scales, bias, residual, ldr, y, ldy, M, int(N), int(K), pdl, stream);
-    set_error("gemv_mma2: unsupported activation dtype %d", dtype);
+                   ? launch_mma_mp<__nv_bfloat16, 8>(x, ldx, wu, scales, bias, residual, ldr, y, ldy, M, int(N), int(K), pdl, stream)
+                   : launch_mma_mp<__nv_bfloat16, 4>(x, ldx, wu, scales, bias, residual, ldr, y, ldy, M, int(N), int(K), pdl, stream);
+    set_error("gemv_mma: unsupported activation dtype %d", dtype);
     return EETQ_B200_EINVAL;
 }
 

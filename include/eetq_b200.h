@@ -58,7 +58,7 @@ enum {
     EETQ_B200_FLAG_FORCE_GEMV = 1, /* force the SIMT streaming kernel (M <= EETQ_B200_GEMV_MAX_M) */
     EETQ_B200_FLAG_FORCE_TC   = 2, /* force the tcgen05 kernel */
     EETQ_B200_FLAG_PDL        = 4, /* launch with programmatic-dependent-launch attribute */
-    EETQ_B200_FLAG_FORCE_MMA2 = 8  /* force the mma.sync streaming kernel with the weights in the A role (M <= 8) */
+    EETQ_B200_FLAG_FORCE_MMA  = 8  /* force the mma.sync streaming kernel (M <= 8) */
 };
 
 #define EETQ_B200_GEMV_MAX_M 8
@@ -265,7 +265,8 @@ int eetq_b200_lm_head_argmax(const void* x, const eetq_b200_ll* x_ll, const void
  * cutlass_preprocessors.cc:389-417).  Packed row-major ("unprocessed") tensors are [K, N/2] bytes, low nibble = even
  * column (cutlass_preprocessors.cc:651-669).
  * ------------------------------------------------------------------------------------------- */
-#define EETQ_B200_GEMV4_MAX_M 4
+#define EETQ_B200_GEMV4_MAX_M 8      /* rows served by the streaming kernels */
+#define EETQ_B200_GEMV4_SIMT_MAX_M 4 /* rows the SIMT kernel takes (K % 128 != 0, or forced) */
 
 /* quant_weights(w, quint4x2): s32[n] = amax[n] * (1/8); q = clamp(int(round_half_away(w / s32[n])), -8, 7), NaN -> -8
  * (bit-exact with ft::symmetric_quantize, cutlass_preprocessors.cc:608-669).  q4_b200: K*N/2 bytes out;
@@ -280,10 +281,11 @@ int eetq_b200_unpack4(const uint8_t* q4_b200, int64_t K, int64_t N, uint8_t* q4_
 int eetq_b200_from_ref_layout4(const uint8_t* w4_ref, int64_t K, int64_t N, uint8_t* q4_b200, void* stream);
 int eetq_b200_to_ref_layout4(const uint8_t* q4_b200, int64_t K, int64_t N, uint8_t* w4_ref, void* stream);
 /* y = dtype( sum_k x[m,k] * q[k,n] * s[n] ) (+ bias) with int4 weights.  M <= EETQ_B200_GEMV4_MAX_M streams the nibbles
- * straight through the decode kernel (half the HBM bytes of w8a16).  Larger M first widens the weights to the b200 int8
- * layout in `workspace` (one extra HBM pass of 1.5 * K*N/1 bytes, negligible next to the tensor-core GEMM it feeds), then
- * runs the tcgen05 kernel: workspace must hold eetq_b200_w4a16_workspace_bytes(M,N,K) bytes (zero-initialised once), else
- * EETQ_B200_EWORKSPACE. */
+ * straight through the decode kernels (half the HBM bytes of w8a16): one row through the SIMT kernel, 2..8 rows through the
+ * mma.sync streaming kernel.  Larger M (or 5..8 rows with K % 128 != 0) first widens the weights to the b200 int8 layout in
+ * `workspace` (one extra HBM pass of 1.5 * K*N bytes, small next to the tensor-core GEMM it feeds), then runs the tcgen05
+ * kernel: workspace must hold eetq_b200_w4a16_workspace_bytes(M,N,K) bytes (zero-initialised once), else
+ * EETQ_B200_EWORKSPACE.  flags: EETQ_B200_FLAG_PDL, FORCE_GEMV (SIMT, M <= 4), FORCE_MMA (M <= 8). */
 size_t eetq_b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int eetq_b200_w4a16_gemm(const void* x, int64_t ldx, const uint8_t* q4_b200, const void* scales, const void* bias, void* y,
                          int64_t ldy, int64_t M, int64_t N, int64_t K, int dtype, void* workspace, size_t workspace_bytes,

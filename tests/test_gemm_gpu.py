@@ -327,14 +327,14 @@ def test_eet_quantize_small_model(cuda, oracle):
 
 @pytest.mark.parametrize("K,N", LLAMA7B + [(64, 64), (5120, 640), (1024, 1728)])
 @pytest.mark.parametrize("M", [1, 2, 3, 4, 6, 8])
-def test_mma2_stream_kernel_matches_oracle(cuda, oracle, K, N, M):
-    """The mma.sync streaming kernel with the weights in the A role (gemv_mma.cu v2), forced through the flag; bias + bf16 on one shape."""
+def test_mma_stream_kernel_matches_oracle(cuda, oracle, K, N, M):
+    """The mma.sync streaming kernel (gemv_mma.cu), forced through the flag for every row count it takes; bias + bf16 on one shape."""
     q, s, wq, sd = make(oracle, cuda, K, N)
     x = oracle.synth_act(M, K)
-    y = w8_a16_gemm_bias(x.to(cuda), wq, sd, None, flags=_cabi.FLAG_FORCE_MMA2)
+    y = w8_a16_gemm_bias(x.to(cuda), wq, sd, None, flags=_cabi.FLAG_FORCE_MMA)
     assert oracle.norm_rel_err(y.cpu(), ref_out(oracle, x, q, s)) <= TOL[torch.float16]
     if (K, N) == (1024, 1728):
         xb = oracle.synth_act(M, K, dtype=torch.bfloat16)
         bias = (torch.randn(N) * 0.1).to(torch.bfloat16)
-        yb = w8_a16_gemm_bias(xb.to(cuda), wq, sd.to(torch.bfloat16), bias.to(cuda), flags=_cabi.FLAG_FORCE_MMA2)
+        yb = w8_a16_gemm_bias(xb.to(cuda), wq, sd.to(torch.bfloat16), bias.to(cuda), flags=_cabi.FLAG_FORCE_MMA)
         assert oracle.norm_rel_err(yb.cpu(), ref_out(oracle, xb, q, s.to(torch.bfloat16), bias)) <= TOL[torch.bfloat16]

@@ -123,9 +123,10 @@ def test_w4a16_gemv_bf16_and_bias(cuda, oracle, M):
 
 
 @pytest.mark.parametrize("K,N", [(4096, 4096), (11008, 4096), (1024, 1728)])
-@pytest.mark.parametrize("M", [5, 16, 64, 300])
+@pytest.mark.parametrize("M", [5, 8, 16, 64, 300])
 def test_w4a16_gemm_batched_matches_oracle(cuda, oracle, K, N, M):
-    """M > 4: nibbles widened to the b200 int8 layout in the workspace, then the tcgen05 kernel (same arithmetic as w8a16)."""
+    """M <= 8: mma.sync streaming kernel; above: nibbles widened to the b200 int8 layout in the workspace, then the tcgen05 kernel
+    (same arithmetic as w8a16)."""
     q, s, wq, sd = make4(oracle, cuda, K, N)
     x = oracle.synth_act(M, K)
     y = eetq_b200.w4_a16_gemm(x.to(cuda).view(1, M, K), wq, sd)
@@ -140,11 +141,12 @@ def test_w4a16_gemm_batched_matches_oracle(cuda, oracle, K, N, M):
 def test_w4a16_needs_workspace_for_large_m(cuda, oracle):
     from eetq_b200 import _cabi
     q, s, wq, sd = make4(oracle, cuda, 256, 128)
-    x = oracle.synth_act(8, 256).to(cuda)
-    y = torch.empty(8, 128, dtype=torch.float16, device=cuda)
+    x = oracle.synth_act(16, 256).to(cuda)
+    y = torch.empty(16, 128, dtype=torch.float16, device=cuda)
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
-    rc = _cabi.lib().eetq_b200_w4a16_gemm(vp(x), 256, vp(wq), vp(sd), None, vp(y), 128, 8, 128, 256, _cabi.F16, None, 0, 0, None)
+    rc = _cabi.lib().eetq_b200_w4a16_gemm(vp(x), 256, vp(wq), vp(sd), None, vp(y), 128, 16, 128, 256, _cabi.F16, None, 0, 0, None)
     assert rc == -4 and b"workspace" in _cabi.lib().eetq_b200_last_error()
+    assert _cabi.lib().eetq_b200_w4a16_workspace_bytes(8, 128, 256) == 0      # up to 8 rows stream through the mma.sync kernel
 
 
 @pytest.mark.parametrize("K,N", LLAMA7B)
@@ -179,14 +181,14 @@ def test_w4a16_against_live_reference_gemv(cuda, oracle, K, N, M):
 @pytest.mark.parametrize("K,N", LLAMA7B + [(128, 64), (8192, 1024), (1024, 1728)])
 @pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8])
 def test_w4a16_mma_stream_kernel_matches_oracle(cuda, oracle, K, N, M):
-    """The mma.sync streaming kernel with the weights in the A role, int4 nibbles (gemv_mma.cu v2), forced through the flag."""
+    """The mma.sync streaming kernel on int4 nibbles (gemv_mma.cu), forced through the flag for every row count it takes."""
     from eetq_b200 import _cabi
     q, s, wq, sd = make4(oracle, cuda, K, N)
     x = oracle.synth_act(M, K)
-    y = eetq_b200.w4_a16_gemm(x.to(cuda), wq, sd, flags=_cabi.FLAG_FORCE_MMA2)
+    y = eetq_b200.w4_a16_gemm(x.to(cuda), wq, sd, flags=_cabi.FLAG_FORCE_MMA)
     assert oracle.norm_rel_err(y.cpu(), ref_out(oracle, x, q, s)) <= TOL[torch.float16]
     if (K, N) == (1024, 1728):
         xb = oracle.synth_act(M, K, dtype=torch.bfloat16)
         bias = (torch.randn(N) * 0.1).to(torch.bfloat16)
-        yb = eetq_b200.w4_a16_gemm(xb.to(cuda), wq, sd.to(torch.bfloat16), bias.to(cuda), flags=_cabi.FLAG_FORCE_MMA2)
+        yb = eetq_b200.w4_a16_gemm(xb.to(cuda), wq, sd.to(torch.bfloat16), bias.to(cuda), flags=_cabi.FLAG_FORCE_MMA)
         assert oracle.norm_rel_err(yb.cpu(), ref_out(oracle, xb, q, s.to(torch.bfloat16), bias)) <= TOL[torch.bfloat16]

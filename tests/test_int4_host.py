@@ -131,6 +131,6 @@ def test_int4_entry_points_validate_without_gpu():
     assert L.eetq_b200_pack4(p, 64, 64, p, None) == -1 and b"in-place" in L.eetq_b200_last_error()
     assert L.eetq_b200_w4a16_gemm(p, 64, p, p, None, p, 64, 0, 64, 64, 0, None, 0, 0, None) == 0      # empty batch
     assert L.eetq_b200_w4a16_gemm(p, 64, p, p, None, p, 64, 1, 64, 64, 7, None, 0, 0, None) == -1     # bad dtype
-    assert L.eetq_b200_w4a16_workspace_bytes(4, 4096, 4096) == 0
+    assert L.eetq_b200_w4a16_workspace_bytes(4, 4096, 4096) == 0      # SIMT rows never need one
     need = L.eetq_b200_w4a16_workspace_bytes(64, 4096, 4096)
     assert need >= 4096 * 4096 + L.eetq_b200_workspace_bytes(64, 4096, 4096)

@@ -44,11 +44,11 @@ def main():
                     if bits == 8:
                         variants["default"] = lambda w: w8_a16_gemm_bias(x, w, sc, None, flags=p)
                         variants["simt"] = lambda w: w8_a16_gemm_bias(x, w, sc, None, flags=p | _cabi.FLAG_FORCE_GEMV)
-                        variants["mma2"] = lambda w: w8_a16_gemm_bias(x, w, sc, None, flags=p | _cabi.FLAG_FORCE_MMA2)
+                        variants["mma2"] = lambda w: w8_a16_gemm_bias(x, w, sc, None, flags=p | _cabi.FLAG_FORCE_MMA)
                     else:
                         if M <= 4:
                             variants["simt"] = lambda w: eetq_b200.w4_a16_gemm(x, w, sc, flags=p | _cabi.FLAG_FORCE_GEMV)
-                        variants["mma2"] = lambda w: eetq_b200.w4_a16_gemm(x, w, sc, flags=p | _cabi.FLAG_FORCE_MMA2)
+                        variants["mma2"] = lambda w: eetq_b200.w4_a16_gemm(x, w, sc, flags=p | _cabi.FLAG_FORCE_MMA)
                     for name, fn in variants.items():
                         med, best = time_graph([(lambda w=w, fn=fn: fn(w)) for w in ws])
                         rec(bits=bits, K=K, N=N, M=M, pdl=pdl, kernel=name, us=round(med, 2), us_best=round(best, 2), gbs=round(algo / med / 1e3, 1))
