@@ -279,12 +279,15 @@ struct WChunk;
 template <>
 struct WChunk<8> {
     using type = uint4;
+    // byte address of 16-k chunk c of row `row`
+    static __device__ __forceinline__ const uint8_t* at(const uint8_t* w, int row, int K, int c) { return w + int64_t(row) * K + int64_t(c) * 16; }
     static __device__ __forceinline__ uint4 load(const uint8_t* p) { return ldg_stream_128(p); }
     static __device__ __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
 };
 template <>
 struct WChunk<4> {
     using type = uint2;
+    static __device__ __forceinline__ const uint8_t* at(const uint8_t* w, int row, int K, int c) { return w + int64_t(row) * (K >> 1) + int64_t(c) * 8; }
     static __device__ __forceinline__ uint2 load(const uint8_t* p)
     {
         uint2 r;
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
                 for (int i = 0; i < KITERS; ++i) {
                     const int c = tid + i * kThreads;
                     if (row < row_end && c < nchunks)
-                        buf[r][i] = WChunk<WB>::load(w + ((int64_t(row) * K + int64_t(c) * 16) * WB >> 3));
+                        buf[r][i] = WChunk<WB>::load(WChunk<WB>::at(w, row, K, c));
                     else
                         buf[r][i] = WChunk<WB>::zero();
                 }
@@ -551,12 +554,17 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
             float acc[M][R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
+                // int4 rows cost 30 instructions per 16 weights and the kernel is issue-bound there (ncu: 60 % issue-active with 4 warps
+                // per scheduler): skip the zero-filled rows of the last group (warp-uniform).  The int8 code is left exactly as measured.
+                const bool live = (WB == 8) || (row_begin + g * R + r < row_end);
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
                     float a = xoff[m];
+                    if (live) {
 #pragma unroll
-                    for (int i = 0; i < KITERS; ++i)
-                        xs[m][i].dot(buf[r][i], a);
+                        for (int i = 0; i < KITERS; ++i)
+                            xs[m][i].dot(buf[r][i], a);
+                    }
                     acc[m][r] = a;
                 }
             }
@@ -593,8 +601,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(M, KITERS, XREG))
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int row = row_begin + g * R + r;
-                    buf[r]        = (row < row_end) ? WChunk<WB>::load(w + ((int64_t(row) * K + int64_t(c) * 16) * WB >> 3))
-                                                    : WChunk<WB>::zero();
+                    buf[r]        = (row < row_end) ? WChunk<WB>::load(WChunk<WB>::at(w, row, K, c)) : WChunk<WB>::zero();
                 }
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
@@ -753,7 +760,7 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
     return EETQ_B200_OK;
 }
 
-template <typename T, int M, int WB>
+template <typename T, int M, int WB, int kRMul>
 int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N, int K,
                const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
@@ -761,8 +768,7 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     const int kiters  = (nchunks + kThreads - 1) / kThreads;
     // register-resident activations while the slice stays small (fp16: 8 regs, bf16: 16 regs per 16 values)
     constexpr int kMaxXregIters = (DTypeOf<T>::value == EETQ_B200_F16) ? 8 / M : 4 / M;
-    // int4 rows are half as long: twice the rows per group keep the same number of bytes in flight per thread
-    constexpr int kRMul = (WB == 4) ? 2 : 1;
+    // kRMul: int4 rows are half as long; twice the rows per group keep the same number of bytes in flight per thread
 #define EB_GEMV_CASE(KI, RS, RB)                                                                                        \
     if (kiters == KI) {                                                                                                 \
         if constexpr (KI <= kMaxXregIters)                                                                             \
@@ -783,28 +789,47 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     return launch_variant<T, M, 1, R, false, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
 }
 
-template <typename T, int WB>
-int dispatch_m(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
-               int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
+template <typename T, int WB, int kRMul>
+int dispatch_m_r(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
+                 int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
     switch (M) {
-        case 1: return dispatch_k<T, 1, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 2: return dispatch_k<T, 2, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 3: return dispatch_k<T, 3, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 4: return dispatch_k<T, 4, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 1: return dispatch_k<T, 1, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 2: return dispatch_k<T, 2, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 3: return dispatch_k<T, 3, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 4: return dispatch_k<T, 4, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
         default: break;
     }
     if constexpr (WB == 8) {
         switch (M) {
-            case 5: return dispatch_k<T, 5, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-            case 6: return dispatch_k<T, 6, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-            case 7: return dispatch_k<T, 7, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-            case 8: return dispatch_k<T, 8, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 5: return dispatch_k<T, 5, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 6: return dispatch_k<T, 6, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 7: return dispatch_k<T, 7, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 8: return dispatch_k<T, 8, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
             default: break;
         }
     }
-    set_error("gemv: M=%d out of range [1,%d]", M, WB == 8 ? EETQ_B200_GEMV_MAX_M : EETQ_B200_GEMV4_MAX_M);
+    set_error("gemv: M=%d out of range [1,%d]", M, WB == 8 ? EETQ_B200_GEMV_MAX_M : EETQ_B200_GEMV4_SIMT_MAX_M);
     return EETQ_B200_EINVAL;
+}
+
+template <typename T, int WB>
+int dispatch_m(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
+               int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
+{
+    if constexpr (WB == 4) {
+        // A/B knob (development): EETQ_B200_GEMV4_R=1 keeps the int8 kernel's rows per group
+        static const bool r1 = [] {
+            const char* e = getenv("EETQ_B200_GEMV4_R");
+            return e != nullptr && e[0] == '1';
+        }();
+        if (r1)
+            return dispatch_m_r<T, 4, 1>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
+        return dispatch_m_r<T, 4, 2>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
+    }
+    else {
+        return dispatch_m_r<T, 8, 1>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
+    }
 }
 
 template <typename T>
