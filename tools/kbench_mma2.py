@@ -29,13 +29,14 @@ def main():
         print(json.dumps(r), flush=True)
         out.append(r)
 
+    only_simt4 = os.environ.get("KBENCH_ONLY_INT4_SIMT") == "1"
     for (K, N) in [(4096, 4096), (4096, 11008), (11008, 4096)]:
-        for bits in (8, 4):
+        for bits in ((4,) if only_simt4 else (8, 4)):
             wbytes = K * N * bits // 8
             pool = max(2, (2 * L2_BYTES) // wbytes + 1)
             ws = [torch.randint(-128, 128, (K, N * bits // 8), dtype=torch.int8, device=dev) for _ in range(pool)]
             sc = (torch.rand(N, device=dev) * 0.01).half()
-            for M in (1, 2, 3, 4, 8):
+            for M in ((1, 2) if only_simt4 else (1, 2, 3, 4, 8)):
                 x = torch.randn(M, K, device=dev).half()
                 algo = wbytes + 2 * N + 2 * M * K + 2 * M * N
                 for pdl in (False, True):
@@ -48,11 +49,12 @@ def main():
                     else:
                         if M <= 4:
                             variants["simt"] = lambda w: eetq_b200.w4_a16_gemm(x, w, sc, flags=p | _cabi.FLAG_FORCE_GEMV)
-                        variants["mma2"] = lambda w: eetq_b200.w4_a16_gemm(x, w, sc, flags=p | _cabi.FLAG_FORCE_MMA)
+                        if not only_simt4:
+                            variants["mma2"] = lambda w: eetq_b200.w4_a16_gemm(x, w, sc, flags=p | _cabi.FLAG_FORCE_MMA)
                     for name, fn in variants.items():
                         med, best = time_graph([(lambda w=w, fn=fn: fn(w)) for w in ws])
                         rec(bits=bits, K=K, N=N, M=M, pdl=pdl, kernel=name, us=round(med, 2), us_best=round(best, 2), gbs=round(algo / med / 1e3, 1))
-                if ref is not None and M <= 4:
+                if ref is not None and M <= 4 and not only_simt4:
                     y = torch.empty(M, N, device=dev, dtype=torch.float16)
                     f = ref.ref_w8a16_gemv if bits == 8 else getattr(ref, "ref_w4a16_gemv", None)
                     if f is not None:
