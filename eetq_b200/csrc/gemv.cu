@@ -818,14 +818,15 @@ int dispatch_m(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
                int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
     if constexpr (WB == 4) {
-        // A/B knob (development): EETQ_B200_GEMV4_R=1 keeps the int8 kernel's rows per group
-        static const bool r1 = [] {
+        // rows per group: the int8 kernel's (measured 2-8 % faster than twice as many, profiles/r02_kbench_mma2.json: the int4 kernel is
+        // issue-bound, not short of bytes in flight); EETQ_B200_GEMV4_R=2 selects the doubled groups for A/B runs
+        static const bool r2 = [] {
             const char* e = getenv("EETQ_B200_GEMV4_R");
-            return e != nullptr && e[0] == '1';
+            return e != nullptr && e[0] == '2';
         }();
-        if (r1)
-            return dispatch_m_r<T, 4, 1>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
-        return dispatch_m_r<T, 4, 2>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
+        if (r2)
+            return dispatch_m_r<T, 4, 2>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
+        return dispatch_m_r<T, 4, 1>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
     }
     else {
         return dispatch_m_r<T, 8, 1>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
