@@ -192,3 +192,13 @@ def test_w4a16_mma_stream_kernel_matches_oracle(cuda, oracle, K, N, M):
         bias = (torch.randn(N) * 0.1).to(torch.bfloat16)
         yb = eetq_b200.w4_a16_gemm(xb.to(cuda), wq, sd.to(torch.bfloat16), bias.to(cuda), flags=_cabi.FLAG_FORCE_MMA)
         assert oracle.norm_rel_err(yb.cpu(), ref_out(oracle, xb, q, s.to(torch.bfloat16), bias)) <= TOL[torch.bfloat16]
+
+
+@pytest.mark.parametrize("M", [2, 4, 6, 8])
+def test_w4a16_k_not_multiple_of_128(cuda, oracle, M):
+    """K % 128 != 0: the mma.sync kernel does not take int4 there -> SIMT up to 4 rows, widen + tcgen05 above."""
+    K, N = 192, 128
+    q, s, wq, sd = make4(oracle, cuda, K, N)
+    x = oracle.synth_act(M, K)
+    y = eetq_b200.w4_a16_gemm(x.to(cuda), wq, sd)
+    assert oracle.norm_rel_err(y.cpu(), ref_out(oracle, x, q, s)) <= TOL[torch.float16]
