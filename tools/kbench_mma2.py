@@ -44,6 +44,7 @@ def main():
                     variants = {}
                     if bits == 8:
                         variants["default"] = lambda w: w8_a16_gemm_bias(x, w, sc, None, flags=p)
+                        # FORCE_GEMV = the streaming kernels: SIMT for 1-2 rows, the mma.sync kernel from 3 rows on (same as "mma2" there)
                         variants["simt"] = lambda w: w8_a16_gemm_bias(x, w, sc, None, flags=p | _cabi.FLAG_FORCE_GEMV)
                         variants["mma2"] = lambda w: w8_a16_gemm_bias(x, w, sc, None, flags=p | _cabi.FLAG_FORCE_MMA)
                     else:
