@@ -944,7 +944,7 @@ TcConfig choose_config(int64_t M, int64_t N, int64_t K, bool have_workspace)
     const int tiles = c.n_tiles * c.t_tiles;
     const int64_t U = int64_t(tiles) * c.spt;
     // Whole tiles per CTA (no partial exchange) win when one wave of tiles already fills most of the machine: the partial dump +
-    // owner fix-up of the stream-K schedule costs a fixed 2-4 us.  Measured cut-offs (kbench, profiles/r02_kbench_tc.jsonl).
+    // owner fix-up of the stream-K schedule costs a fixed 2-4 us.  Measured cut-offs (kbench, profiles/r02_kbench_tc.json).
     {
         const int waves   = (tiles + sms - 1) / sms;
         const double fill = double(tiles) / (double(waves) * sms);

@@ -338,10 +338,6 @@ template <>
 struct Log2<8> {
     static constexpr int v = 3;
 };
-template <>
-struct Log2<16> {
-    static constexpr int v = 4;
-};
 
 // dynamic smem: partial[row][m][warp] fp32
 extern __shared__ float gemv_partial[];
@@ -760,7 +756,7 @@ int launch_variant(const T* x, int64_t ldx, const uint8_t* w, const T* scales, c
     return EETQ_B200_OK;
 }
 
-template <typename T, int M, int WB, int kRMul>
+template <typename T, int M, int WB>
 int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int N, int K,
                const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
@@ -768,12 +764,13 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     const int kiters  = (nchunks + kThreads - 1) / kThreads;
     // register-resident activations while the slice stays small (fp16: 8 regs, bf16: 16 regs per 16 values)
     constexpr int kMaxXregIters = (DTypeOf<T>::value == EETQ_B200_F16) ? 8 / M : 4 / M;
-    // kRMul: int4 rows are half as long; twice the rows per group keep the same number of bytes in flight per thread
+    // rows per group are the same for int8 and int4: doubling them for the half-as-long int4 rows (same bytes in flight) measured
+    // 2-8 % slower (more zero-padded rows; the int4 kernel is issue-bound, profiles/r02_kbench_int4_simt_rows8.json)
 #define EB_GEMV_CASE(KI, RS, RB)                                                                                        \
     if (kiters == KI) {                                                                                                 \
         if constexpr (KI <= kMaxXregIters)                                                                             \
-            return launch_variant<T, M, KI, kRMul * (M <= 2 ? RS : RB), true, WB>(x, ldx, w, scales, bias, y, ldy, N, K,   \
-                                                                                  fuse, pdl, stream);                   \
+            return launch_variant<T, M, KI, (M <= 2 ? RS : RB), true, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse,  \
+                                                                          pdl, stream);                                  \
     }
     EB_GEMV_CASE(1, 8, 4)
     EB_GEMV_CASE(2, 4, 2)
@@ -789,48 +786,28 @@ int dispatch_k(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const
     return launch_variant<T, M, 1, R, false, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
 }
 
-template <typename T, int WB, int kRMul>
-int dispatch_m_r(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
-                 int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
+template <typename T, int WB>
+int dispatch_m(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
+               int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
 {
     switch (M) {
-        case 1: return dispatch_k<T, 1, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 2: return dispatch_k<T, 2, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 3: return dispatch_k<T, 3, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-        case 4: return dispatch_k<T, 4, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 1: return dispatch_k<T, 1, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 2: return dispatch_k<T, 2, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 3: return dispatch_k<T, 3, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+        case 4: return dispatch_k<T, 4, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
         default: break;
     }
     if constexpr (WB == 8) {
         switch (M) {
-            case 5: return dispatch_k<T, 5, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-            case 6: return dispatch_k<T, 6, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-            case 7: return dispatch_k<T, 7, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
-            case 8: return dispatch_k<T, 8, WB, kRMul>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 5: return dispatch_k<T, 5, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 6: return dispatch_k<T, 6, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 7: return dispatch_k<T, 7, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
+            case 8: return dispatch_k<T, 8, WB>(x, ldx, w, scales, bias, y, ldy, N, K, fuse, pdl, stream);
             default: break;
         }
     }
     set_error("gemv: M=%d out of range [1,%d]", M, WB == 8 ? EETQ_B200_GEMV_MAX_M : EETQ_B200_GEMV4_SIMT_MAX_M);
     return EETQ_B200_EINVAL;
-}
-
-template <typename T, int WB>
-int dispatch_m(const T* x, int64_t ldx, const uint8_t* w, const T* scales, const T* bias, T* y, int64_t ldy, int M, int N,
-               int K, const GemvFuse<T>& fuse, bool pdl, cudaStream_t stream)
-{
-    if constexpr (WB == 4) {
-        // rows per group: the int8 kernel's (measured 2-8 % faster than twice as many, profiles/r02_kbench_mma2.json: the int4 kernel is
-        // issue-bound, not short of bytes in flight); EETQ_B200_GEMV4_R=2 selects the doubled groups for A/B runs
-        static const bool r2 = [] {
-            const char* e = getenv("EETQ_B200_GEMV4_R");
-            return e != nullptr && e[0] == '2';
-        }();
-        if (r2)
-            return dispatch_m_r<T, 4, 2>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
-        return dispatch_m_r<T, 4, 1>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
-    }
-    else {
-        return dispatch_m_r<T, 8, 1>(x, ldx, w, scales, bias, y, ldy, M, N, K, fuse, pdl, stream);
-    }
 }
 
 template <typename T>
