@@ -200,28 +200,15 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
 
     int c_tile = 0, c_j = 0;  // consumer state
-    // kAcc independent accumulator sets, used round-robin: a single set makes every MMA of the warp wait for the one before it
-    // (96 dependent mma.sync per warp on 4096 x 11008, the same count for int8 and int4 -- which is why both took the same time)
-    constexpr int kAcc = 4;
-    float acc[kAcc][4];
-#pragma unroll
-    for (int a = 0; a < kAcc; ++a)
-        acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
-    // D fragment: [0..1] = (feature g, tokens 2t, 2t+1), [2..3] = (feature g + 8, tokens 2t, 2t+1)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // D fragment: acc[0..1] = (feature g, tokens 2t, 2t+1), acc[2..3] = (feature g + 8, tokens 2t, 2t+1)
     auto flush = [&](int tile) {
-        float d[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            d[i] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
-#pragma unroll
-            for (int a = 0; a < kAcc; ++a)
-                acc[a][i] = 0.f;
-        }
         if (2 * t < MP) {
             float* base = partial + (warp * max_tiles + tile) * 16 * MP;
-            *reinterpret_cast<float2*>(base + g * MP + 2 * t)       = make_float2(d[0], d[1]);
-            *reinterpret_cast<float2*>(base + (g + 8) * MP + 2 * t) = make_float2(d[2], d[3]);
+            *reinterpret_cast<float2*>(base + g * MP + 2 * t)       = make_float2(acc[0], acc[1]);
+            *reinterpret_cast<float2*>(base + (g + 8) * MP + 2 * t) = make_float2(acc[2], acc[3]);
         }
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
     };
     auto compute_buf = [&](const uint4 (&buf)[kBuf], int count) {
 #pragma unroll
@@ -239,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                         uint2 xv = make_uint2(0u, 0u);
                         if (g < MP)
                             xv = *reinterpret_cast<const uint2*>(xrow + jj * 8);
-                        mma_16816<T>(acc[jj], a, xv.x, xv.y);
+                        mma_16816<T>(acc, a, xv.x, xv.y);
                     }
                     else {
 #pragma unroll
@@ -252,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                             uint2 xv = make_uint2(0u, 0u);
                             if (g < MP)
                                 xv = *reinterpret_cast<const uint2*>(xrow + jj * 16 + h * 8);
-                            mma_16816<T>(acc[(2 * jj + h) & 3], a, xv.x, xv.y);
+                            mma_16816<T>(acc, a, xv.x, xv.y);
                         }
                     }
                 }
