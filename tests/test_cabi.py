@@ -93,3 +93,19 @@ def test_python_surface_fails_loudly_without_gpu():
         eetq_b200.w8_a16_gemm(x, w, s)
     with pytest.raises(RuntimeError, match="CUDA|sm_100"):
         eetq_b200.quant_weights(torch.zeros(64, 64, dtype=torch.float16), torch.int8, False)
+
+
+def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
+    """include/eetq_b200.h compiles as C99 (the boundary is a C ABI, not a C++ one) and a C program linked against the
+    library can call it (validation paths only: no device needed)."""
+    import subprocess
+
+    from eetq_b200 import _cabi
+
+    src = os.path.join(ROOT, "tests", "host", "abi_check.c")
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-o", exe, src, "-L" + libdir, "-leetq_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
