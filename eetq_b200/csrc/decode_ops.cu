@@ -847,6 +847,8 @@ extern "C" {
 int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, int64_t H, const eetq_b200_ll* x_ll, int pdl, void* stream)
 {
     EB_CHECK_ARG(table && token_i64 && x && H % 8 == 0, "decode_embed: bad argument");
+    if (int rc = check_arch())
+        return rc;
     LLTag tag{};
     if (x_ll != nullptr && x_ll->step != nullptr) {
         tag.tag_base = static_cast<const int*>(x_ll->step);
@@ -865,6 +867,8 @@ int eetq_b200_decode_embed(const void* table, const void* token_i64, void* x, in
 int eetq_b200_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int64_t M, int64_t H, float eps, int pdl, void* stream)
 {
     EB_CHECK_ARG(x && w && y && M > 0 && H > 0 && ldx >= H && ldy >= H, "rmsnorm: bad argument");
+    if (int rc = check_arch())
+        return rc;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
     launch_cfg(cfg, attr, dim3(unsigned(M)), dim3(512), 0, pdl != 0, static_cast<cudaStream_t>(stream));
@@ -878,6 +882,8 @@ int eetq_b200_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_
 int eetq_b200_layernorm_forward(const void* input, const void* gamma, void* out, int64_t m, int64_t n, float eps, void* stream)
 {
     EB_CHECK_ARG(input && gamma && out && m > 0 && n > 0, "layernorm_forward: bad argument");
+    if (int rc = check_arch())
+        return rc;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
     launch_cfg(cfg, attr, dim3(unsigned(m)), dim3(512), 0, false, static_cast<cudaStream_t>(stream));
@@ -894,6 +900,8 @@ int eetq_b200_rotary_embedding_neox(const void* positions_i64, void* query, void
     EB_CHECK_ARG(positions_i64 && query && key && cos_sin_cache, "rotary_embedding_neox: null pointer argument");
     EB_CHECK_ARG(num_tokens > 0 && num_heads > 0 && head_size > 0 && rot_dim > 0 && rot_dim % 2 == 0 && rot_dim <= head_size,
                  "rotary_embedding_neox: bad shape");
+    if (int rc = check_arch())
+        return rc;
     const int threads = int(num_heads * rot_dim / 2 < 512 ? num_heads * rot_dim / 2 : 512);
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
@@ -910,6 +918,8 @@ int eetq_b200_prefill_rope_kv(void* qkv, int64_t ld, const void* cos_t, const vo
 {
     EB_CHECK_ARG(qkv && cos_t && sin_t && kcache && vcache && T > 0 && heads > 0 && D > 0 && D % 2 == 0, "prefill_rope_kv: bad argument");
     EB_CHECK_ARG(p0 >= 0 && p0 + T <= max_ctx && ld >= 3 * heads * D, "prefill_rope_kv: positions exceed the cache or bad stride");
+    if (int rc = check_arch())
+        return rc;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
     launch_cfg(cfg, attr, dim3(unsigned(T), unsigned(heads)), dim3(128), 0, false, static_cast<cudaStream_t>(stream));
@@ -923,6 +933,8 @@ int eetq_b200_prefill_rope_kv(void* qkv, int64_t ld, const void* cos_t, const vo
 int eetq_b200_silu_mul(const void* gu, int64_t ldg, void* act, int64_t lda, int64_t T, int64_t I, int interleaved, void* stream)
 {
     EB_CHECK_ARG(gu && act && T > 0 && I > 0 && ldg >= 2 * I && lda >= I, "silu_mul: bad argument");
+    if (int rc = check_arch())
+        return rc;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
     launch_cfg(cfg, attr, dim3(unsigned((I + 255) / 256), unsigned(T)), dim3(256), 0, false, static_cast<cudaStream_t>(stream));
@@ -945,6 +957,8 @@ int eetq_b200_decode_attention(const void* qkv, const void* cos_t, const void* s
     EB_CHECK_ARG((out != nullptr) != (push != nullptr), "decode_attention: exactly one of out / push must be given");
     EB_CHECK_ARG(D == ATT_D && H_local % D == 0 && H_local > 0, "decode_attention: head_dim must be 128");
     EB_CHECK_ARG(max_ctx >= 1 && max_ctx <= (1 << 20), "decode_attention: bad max_ctx");
+    if (int rc = check_arch())
+        return rc;
     AttnOut ao{};
     ao.out = static_cast<__half*>(out);
     if (push != nullptr) {
@@ -1006,6 +1020,8 @@ int eetq_b200_lm_head_argmax(const void* x, const eetq_b200_ll* x_ll, const void
     EB_CHECK_ARG(x && norm_w && w && scratch && token_i64 && pos_i32 && step_i32, "lm_head_argmax: null pointer argument");
     EB_CHECK_ARG(V_local > 0 && H > 0 && H % 8 == 0 && H <= LM_MAXKI * LM_THREADS * 8, "lm_head_argmax: bad shape (hidden <= %d)",
                  LM_MAXKI * LM_THREADS * 8);
+    if (int rc = check_arch())
+        return rc;
     const DeviceInfo& di = device_info();
     EB_CHECK_ARG(di.ok, "lm_head_argmax: device query failed");
     int grid = di.sm_count * 2;

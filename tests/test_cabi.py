@@ -109,3 +109,18 @@ def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
                     "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_decode_entry_points_refuse_to_launch_without_sm100(lib):
+    """every forward entry point checks the device before launching (error code + message, never a launch failure)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    buf = ctypes.create_string_buffer(1 << 16)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.eetq_b200_rmsnorm(p, 64, p, p, 64, 1, 64, ctypes.c_float(1e-5), 0, None) in (-2, -3)
+    assert lib.eetq_b200_layernorm_forward(p, p, p, 1, 64, ctypes.c_float(1e-5), None) in (-2, -3)
+    assert lib.eetq_b200_silu_mul(p, 128, p, 64, 1, 64, 0, None) in (-2, -3)
+    assert lib.eetq_b200_decode_embed(p, p, p, 64, None, 0, None) in (-2, -3)
+    assert b"device" in lib.eetq_b200_last_error()
