@@ -18,8 +18,8 @@ timeout 600 ncu --set full --clock-control none --import-source on --profile-fro
 timeout 400 python tools/kbench.py --tc-only --out $O/kb_tc.json > $O/kb_tc.log 2>&1
 timeout 300 python tools/kbench_smallm.py > $O/kbench_smallm.log 2>&1
 EETQ_B200_LIB=$PWD/eetq_b200/libeetq_b200_trace.so timeout 300 python tools/timeline.py --layers 4 > $O/timeline.log 2>&1
-timeout 200 compute-sanitizer --tool racecheck python tools/tc_debug.py --tiny > $O/sanitizer_racecheck.log 2>&1; echo "rc=$?" >> $O/sanitizer_racecheck.log
-timeout 200 compute-sanitizer --tool synccheck python tools/tc_debug.py --tiny > $O/sanitizer_synccheck.log 2>&1; echo "rc=$?" >> $O/sanitizer_synccheck.log
+timeout 200 compute-sanitizer --tool racecheck python tests/diag/tc_debug.py --tiny > $O/sanitizer_racecheck.log 2>&1; echo "rc=$?" >> $O/sanitizer_racecheck.log
+timeout 200 compute-sanitizer --tool synccheck python tests/diag/tc_debug.py --tiny > $O/sanitizer_synccheck.log 2>&1; echo "rc=$?" >> $O/sanitizer_synccheck.log
 tail -n 3 $O/t_all.log $O/smoke.log
 cut -c1-700 $O/bench_ref.json; tail -n 2 $O/bench_ref.err
 cat $O/bench_n1.json; tail -n 2 $O/bench_n1.err
