@@ -1,5 +1,5 @@
 """w4a16 kernel micro-benchmark (development tool): our int4 decode kernel, the widen + tcgen05 path, and the reference's Int4b
-decode kernel rebuilt for sm_100a, timed like tools/kbench.py (CUDA-graph replays cycling > 2x L2 of distinct weights)."""
+decode kernel rebuilt for sm_100a, timed like kbench.py (CUDA-graph replays cycling > 2x L2 of distinct weights)."""
 import ctypes
 import json
 import os
@@ -7,9 +7,9 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import eetq_b200  # noqa: E402
 from kbench import L2_BYTES, time_graph  # noqa: E402
 

@@ -1,5 +1,5 @@
 """A/B micro-benchmark of the decode-row kernels (development tool): SIMT / token-major mma.sync / weights-in-A mma.sync (v2) for
-int8 and int4 weights, plus the reference kernels rebuilt for sm_100a; timed like tools/kbench.py."""
+int8 and int4 weights, plus the reference kernels rebuilt for sm_100a; timed like kbench.py."""
 import ctypes
 import json
 import os
@@ -7,9 +7,9 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import eetq_b200  # noqa: E402
 from eetq_b200 import _cabi  # noqa: E402
 from eetq_b200.ops import w8_a16_gemm_bias  # noqa: E402

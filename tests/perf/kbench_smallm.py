@@ -1,11 +1,12 @@
 """Where should the dispatch cut between the SIMT streaming kernel and the tcgen05 kernel sit?  Times M = 4..16."""
 import json, os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from eetq_b200 import _cabi
 from eetq_b200.ops import w8_a16_gemm_bias
-from tools.kbench import time_graph, algo_bytes, L2_BYTES
+from kbench import time_graph, algo_bytes, L2_BYTES
 dev = torch.device("cuda", 0); torch.cuda.set_device(dev)
 for (K, N) in [(4096, 4096), (4096, 11008), (11008, 4096)]:
     pool = max(2, (2 * L2_BYTES) // (K * N) + 1)

@@ -15,8 +15,8 @@ BENCH_PROFILE_RANGE=1 timeout 600 ncu --set full --clock-control none --import-s
 BENCH_PROFILE_RANGE=1 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_decode -c 2 \
     -o $O/prof_attn -f python bench.py --steps 1 --warmup 1 --skip-cpu-baseline --layers 2 > $O/ncu_attn.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_tc -o $O/prof_tc -f python tools/prof_tc.py > $O/ncu_tc.log 2>&1
-timeout 400 python tools/kbench.py --tc-only --out $O/kb_tc.json > $O/kb_tc.log 2>&1
-timeout 300 python tools/kbench_smallm.py > $O/kbench_smallm.log 2>&1
+timeout 400 python tests/perf/kbench.py --tc-only --out $O/kb_tc.json > $O/kb_tc.log 2>&1
+timeout 300 python tests/perf/kbench_smallm.py > $O/kbench_smallm.log 2>&1
 EETQ_B200_LIB=$PWD/eetq_b200/libeetq_b200_trace.so timeout 300 python tools/timeline.py --layers 4 > $O/timeline.log 2>&1
 timeout 200 compute-sanitizer --tool racecheck python tests/diag/tc_debug.py --tiny > $O/sanitizer_racecheck.log 2>&1; echo "rc=$?" >> $O/sanitizer_racecheck.log
 timeout 200 compute-sanitizer --tool synccheck python tests/diag/tc_debug.py --tiny > $O/sanitizer_synccheck.log 2>&1; echo "rc=$?" >> $O/sanitizer_synccheck.log

@@ -10,5 +10,5 @@ timeout 300 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "rc=$?" 
 cat $O/bench_n1.json; tail -n 2 $O/bench_n1.err
 timeout 300 python bench.py --impl reference --steps 8 --warmup 3 > $O/bench_ref.json 2> $O/bench_ref.err; echo "rc=$?" >> $O/bench_ref.err
 cut -c1-600 $O/bench_ref.json; tail -n 2 $O/bench_ref.err
-timeout 200 python tools/kbench_mma2.py > $O/kbench_mma2.log 2>&1; echo "rc=$?" >> $O/kbench_mma2.log
+timeout 200 python tests/perf/kbench_mma2.py > $O/kbench_mma2.log 2>&1; echo "rc=$?" >> $O/kbench_mma2.log
 tail -n 2 $O/kbench_mma2.log
