@@ -29,12 +29,14 @@ import torch
 from torch import nn
 from torch.autograd import Function
 
-from ..ops import convert_ref_checkpoint_weight, preprocess_weights, quant_weights, to_ref_checkpoint_weight, w8_a16_gemm, w8_a16_gemm_bias
+from ..ops import (convert_ref_checkpoint_weight, convert_ref_checkpoint_weight4, preprocess_weights, quant_weights, to_ref_checkpoint_weight,
+                   to_ref_checkpoint_weight4, w4_a16_gemm, w8_a16_gemm, w8_a16_gemm_bias)
 
-__all__ = ["quantize_and_preprocess_weights", "W8A16Linear", "EetqLinearMMFunction", "EetqLinear", "B200_LAYOUT",
-           "export_reference_state_dict"]
+__all__ = ["quantize_and_preprocess_weights", "W8A16Linear", "W4A16Linear", "EetqLinearMMFunction", "EetqLinear", "B200_LAYOUT",
+           "B200_LAYOUT_INT4", "export_reference_state_dict"]
 
-B200_LAYOUT = 200   # value of the ``weight_layout`` marker: bytes are output-feature-major, biased
+B200_LAYOUT = 200        # value of the ``weight_layout`` marker: bytes are output-feature-major, biased
+B200_LAYOUT_INT4 = 204   # same for packed int4: rows of K/2 bytes, nibbles interleaved inside every 32-bit word
 _LAYOUT_KEY = "weight_layout"
 
 
@@ -42,9 +44,17 @@ class _LayoutAwareMixin:
     """``load_state_dict`` support shared by W8A16Linear / EetqLinear: convert reference-layout weights, check the marker."""
 
     _weight_key = "qweight"
+    _layout_value = B200_LAYOUT
+
+    # reference-layout bytes <-> this module's layout (GPU kernels; looked up at call time so that tests can stub them)
+    def _from_ref(self, w: torch.Tensor) -> torch.Tensor:
+        return convert_ref_checkpoint_weight(w)
+
+    def _to_ref(self, w: torch.Tensor) -> torch.Tensor:
+        return to_ref_checkpoint_weight(w)
 
     def _register_layout_marker(self, device) -> None:
-        self.register_buffer(_LAYOUT_KEY, torch.tensor([B200_LAYOUT], dtype=torch.int32, device=device))
+        self.register_buffer(_LAYOUT_KEY, torch.tensor([self._layout_value], dtype=torch.int32, device=device))
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
         wkey, lkey = prefix + self._weight_key, prefix + _LAYOUT_KEY
@@ -61,12 +71,13 @@ class _LayoutAwareMixin:
                                            "(eetq_b200 has no CPU path)")
                     src = w if w.is_cuda else w.cuda()
                     state_dict = dict(state_dict)  # do not touch the caller's dict
-                    state_dict[wkey] = convert_ref_checkpoint_weight(src.contiguous()).to(w.device)
-                    state_dict[lkey] = torch.tensor([B200_LAYOUT], dtype=torch.int32)
+                    state_dict[wkey] = self._from_ref(src.contiguous()).to(w.device)
+                    state_dict[lkey] = torch.tensor([self._layout_value], dtype=torch.int32)
             else:
                 marker = int(state_dict[lkey].reshape(-1)[0])
-                if marker != B200_LAYOUT:
-                    error_msgs.append(f"{lkey} = {marker}: unknown weight layout (this build understands {B200_LAYOUT})")
+                if marker != self._layout_value:
+                    error_msgs.append(f"{lkey} = {marker}: weight layout does not match this module (expected {self._layout_value}; "
+                                      f"{B200_LAYOUT} = int8, {B200_LAYOUT_INT4} = packed int4)")
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
 
@@ -80,7 +91,7 @@ def export_reference_state_dict(model: nn.Module) -> dict:
             wkey = prefix + mod._weight_key
             w = sd[wkey]
             src = w if w.is_cuda else w.cuda()
-            sd[wkey] = to_ref_checkpoint_weight(src.contiguous()).to(w.device)
+            sd[wkey] = mod._to_ref(src.contiguous()).to(w.device)
             sd.pop(prefix + _LAYOUT_KEY, None)
     return sd
 
@@ -149,6 +160,62 @@ class W8A16Linear(_LayoutAwareMixin, nn.Module):
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"
+
+
+class W4A16Linear(_LayoutAwareMixin, nn.Module):
+    """Weight-only packed-int4 linear layer.  The reference has no int4 module: its Python reaches int4 only through
+    ``quant_weights(w, torch.quint4x2)`` / ``preprocess_weights(w, is_int4=True)`` (csrc/eetpy.cpp:11-17) and its wrapper never selects
+    the Int4b kernels it compiles (fpA_intB_gemm_wrapper.cu:154-159).  This module puts those two calls and ``w4_a16_gemm`` behind the
+    ``W8A16Linear`` surface: ``qweight`` int8 ``[in, out/2]`` (two values per byte, b200 int4 layout), ``weight_scales`` ``[out]``,
+    optional ``bias``; a state dict without the layout marker is taken to hold the reference's processed int4 bytes and converted."""
+
+    _weight_key = "qweight"
+    _layout_value = B200_LAYOUT_INT4
+
+    def _from_ref(self, w: torch.Tensor) -> torch.Tensor:
+        return convert_ref_checkpoint_weight4(w)
+
+    def _to_ref(self, w: torch.Tensor) -> torch.Tensor:
+        return to_ref_checkpoint_weight4(w)
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, dev="cuda:0", dtype: torch.dtype = torch.float16):
+        super().__init__()
+        if in_features % 64 or out_features % 64:
+            raise ValueError("W4A16Linear needs in_features and out_features to be multiples of 64")
+        self.in_features, self.out_features = in_features, out_features
+        self.register_buffer("qweight", torch.zeros(in_features, out_features // 2, dtype=torch.int8, device=dev))
+        self._register_layout_marker(dev)
+        self.register_buffer("weight_scales", torch.zeros(out_features, dtype=dtype, device=dev))
+        if bias:
+            self.register_buffer("bias", torch.zeros(out_features, dtype=dtype, device=dev))
+        else:
+            self.bias = None
+
+    @classmethod
+    def from_torch(cls, linear: nn.Module, init_only: bool = False) -> "W4A16Linear":
+        target = linear.weight.device
+        act = _activation_dtype_for(linear.weight.dtype)
+        layer = cls(linear.in_features, linear.out_features, bias=linear.bias is not None, dev=target, dtype=act)
+        if init_only:
+            return layer
+        source = linear.weight.detach()
+        if source.dtype not in _FLOAT_WEIGHT_DTYPES:
+            raise ValueError("Unsupported data type: {}".format(source.dtype))
+        if not source.is_cuda and torch.cuda.is_available():
+            source = source.cuda()  # the quantiser is a GPU kernel; results go back to `target` below
+        packed, scales = quant_weights(source.t().contiguous(), torch.quint4x2, False)
+        layer.qweight = packed.to(target)
+        layer.weight_scales = scales.to(act).to(target)
+        if linear.bias is not None:
+            layer.bias = linear.bias.detach().to(act).clone()
+        return layer
+
+    @torch.no_grad()
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return w4_a16_gemm(input, self.qweight, self.weight_scales, self.bias)
+
+    def extra_repr(self) -> str:
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, bits=4"
 
 
 class EetqLinearMMFunction(Function):

@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from ..modules.qlinear import W8A16Linear
+from ..modules.qlinear import W4A16Linear, W8A16Linear
 from .base import find_layers, find_submodule, get_named_linears, set_op_by_name
 
 __all__ = ["eet_quantize", "replace_with_eet_qlinear", "structure_mapping"]
@@ -26,8 +26,14 @@ def structure_mapping(model: nn.Module, target_model: str = "llama") -> dict:
         raise NotImplementedError(f"structure_mapping: unsupported model family {target_model!r}") from None
 
 
-def _to_w8a16(linear: nn.Module, init_only: bool) -> W8A16Linear:
+def _to_w8a16(linear: nn.Module, init_only: bool, bits: int = 8) -> nn.Module:
     wdtype = linear.weight.dtype
+    if bits == 4:  # our extension: packed int4 (the reference's eet_quantize only knows int8)
+        if wdtype not in (torch.float16, torch.bfloat16, torch.float32):
+            raise ValueError("Unsupported data type: {}".format(wdtype))
+        return W4A16Linear.from_torch(linear, init_only=init_only)
+    if bits != 8:
+        raise ValueError(f"eet_quantize: bits must be 8 or 4 (got {bits})")
     if wdtype == torch.int8:
         # bitsandbytes.nn.Linear8bitLt keeps per-output-row abs-max in SCB; its int8 code is w / SCB * 127
         scales = linear.state_dict()["SCB"] / 127.0
@@ -38,13 +44,13 @@ def _to_w8a16(linear: nn.Module, init_only: bool) -> W8A16Linear:
 
 
 def eet_quantize(model: nn.Module, init_only: bool = False, include=(nn.Linear,), exclude=("lm_head",), device="cuda:0",
-                 verbose: bool = False) -> nn.Module:
+                 verbose: bool = False, bits: int = 8) -> nn.Module:
     """Quantise ``model`` in place and return it.  ``init_only=True`` builds the quantised skeleton without touching the
     weights (for loading an already-quantised checkpoint).  ``device`` is accepted for signature compatibility; each layer
-    stays on the device its weight lives on."""
+    stays on the device its weight lives on.  ``bits=4`` (extension) swaps in :class:`W4A16Linear` instead."""
     targets = find_layers(model, include=include, exclude=exclude)
     for dotted_name, linear in targets.items():
-        set_op_by_name(model, dotted_name, _to_w8a16(linear, init_only))
+        set_op_by_name(model, dotted_name, _to_w8a16(linear, init_only, bits))
         if verbose:
             print("[EET][INFO] quantized {}".format(dotted_name))
     return model

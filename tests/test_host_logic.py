@@ -110,7 +110,7 @@ def test_state_dict_layout_marker_decides_conversion(monkeypatch, cls, key):
 
     bad = dict(sd)
     bad["weight_layout"] = torch.tensor([7], dtype=torch.int32)
-    with pytest.raises(RuntimeError, match="unknown weight layout"):
+    with pytest.raises(RuntimeError, match="weight layout does not match"):
         cls(64, 64, bias=False, **kw).load_state_dict(bad, strict=False)
 
 
@@ -191,3 +191,27 @@ def test_reference_package_names_resolve():
     from EETQ import preprocess_weights, quant_weights, w8_a16_gemm  # noqa: F401
 
     assert A is eetq_b200.W8A16Linear and q is eetq_b200.eet_quantize and eetq.EetqLinear is eetq_b200.EetqLinear
+
+
+def test_w4a16_module_surface_and_layout_marker():
+    """W4A16Linear (extension): packed [in, out/2] buffer, its own layout marker, eet_quantize(bits=4) swaps it in; a state dict of
+    the other bit width is refused instead of being mis-read."""
+    from eetq_b200 import W4A16Linear
+
+    m = nn.Sequential(nn.Linear(128, 64), nn.Linear(64, 128, bias=False))
+    eetq_b200.eet_quantize(m, init_only=True, bits=4)
+    assert isinstance(m[0], W4A16Linear) and isinstance(m[1], W4A16Linear)
+    sd = m.state_dict()
+    assert sd["0.qweight"].shape == (128, 32) and sd["0.qweight"].dtype == torch.int8
+    assert int(sd["0.weight_layout"][0]) == eetq_b200.B200_LAYOUT_INT4 and "1.bias" not in sd
+    q4 = W4A16Linear(128, 64, bias=True, dev="cpu")
+    q4.load_state_dict({k[2:]: v for k, v in sd.items() if k.startswith("0.")})          # same layout: loads as is
+    q8 = W8A16Linear(128, 64, bias=True, dev="cpu")
+    bad = dict(q8.state_dict())
+    bad["qweight"] = torch.zeros(128, 32, dtype=torch.int8)
+    with pytest.raises(RuntimeError, match="weight layout does not match"):
+        q4.load_state_dict(bad)                                                           # int8 marker into an int4 module
+    with pytest.raises(ValueError, match="bits must be 8 or 4"):
+        eetq_b200.eet_quantize(nn.Sequential(nn.Linear(64, 64)), init_only=True, bits=3)
+    with pytest.raises(ValueError, match="multiples of 64"):
+        W4A16Linear(100, 64, dev="cpu")

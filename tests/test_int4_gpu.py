@@ -202,3 +202,32 @@ def test_w4a16_k_not_multiple_of_128(cuda, oracle, M):
     x = oracle.synth_act(M, K)
     y = eetq_b200.w4_a16_gemm(x.to(cuda), wq, sd)
     assert oracle.norm_rel_err(y.cpu(), ref_out(oracle, x, q, s)) <= TOL[torch.float16]
+
+
+def test_w4a16_module_end_to_end(cuda, oracle):
+    """W4A16Linear.from_torch = quant_weights(w.T, quint4x2) + fused-bias w4_a16_gemm; reference-layout int4 bytes load through the
+    state-dict hook and export writes them back."""
+    import torch.nn as nn
+    from eetq_b200.modules.qlinear import export_reference_state_dict
+    lin = nn.Linear(1024, 512, bias=True).half().to(cuda)
+    ql = eetq_b200.W4A16Linear.from_torch(lin)
+    packed, s, _, q = oracle.quantize4(lin.weight.detach().t().contiguous().cpu())
+    assert torch.equal(ql.qweight.cpu(), oracle.b200_layout4(q)) and torch.equal(ql.weight_scales.cpu(), s)
+    for M in (1, 3, 40):
+        x = oracle.synth_act(M, 1024).to(cuda)
+        y_ref = oracle.gemm(x.cpu(), q, s, lin.bias.detach().cpu())
+        assert oracle.norm_rel_err(ql(x).cpu(), y_ref) <= 1e-3
+    # a state dict WITHOUT the marker holds the reference's processed int4 bytes
+    ref_sd = {"qweight": oracle.ref_layout4(q), "weight_scales": s, "bias": lin.bias.detach().cpu()}
+    q2 = eetq_b200.W4A16Linear(1024, 512, bias=True, dev=cuda)
+    q2.load_state_dict(ref_sd)
+    assert torch.equal(q2.qweight.cpu(), ql.qweight.cpu())
+    out = export_reference_state_dict(q2)
+    assert torch.equal(out["qweight"].cpu(), ref_sd["qweight"]) and "weight_layout" not in out
+    # eet_quantize(bits=4) on a small model
+    m = nn.Sequential(nn.Linear(256, 128), nn.Linear(128, 64)).half().to(cuda)
+    x = oracle.synth_act(2, 256).to(cuda)
+    y_fp = m(x)
+    eetq_b200.eet_quantize(m, bits=4)
+    assert isinstance(m[0], eetq_b200.W4A16Linear)
+    assert (m(x) - y_fp).abs().max() <= 0.25 * y_fp.abs().max()     # int4 quantisation noise, two layers deep
