@@ -220,7 +220,7 @@ int gemm_dispatch(const void* x, int64_t ldx, const int8_t* w_b200, const void* 
         return launch_gemv_mma(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, 8, pdl, s);
     }
     // 3..8 rows: the mma.sync streaming kernel (M-independent instruction count); 1 and 2 rows: the SIMT kernel measured faster
-    // (profiles/r02_kbench_mma2.json: 4096x4096 M = 3 / 4: 8.1 / 8.2 us vs 8.7 / 8.9 SIMT)
+    // (A/B runs of this round, DESIGN.md section 5: 4096x4096 M = 3 / 4: 8.1-8.6 us vs 8.7 / 8.9 us SIMT)
     if (use_gemv && M >= 3 && gemv_mma_on() && gemv_mma_supported(int(M), K, 8))
         return launch_gemv_mma(x, ldx, w_b200, scales, bias, residual, ldr, y, ldy, int(M), N, K, dtype, 8, pdl, s);
     if (use_gemv) {
@@ -418,8 +418,8 @@ int eetq_b200_w4a16_gemm(const void* x, int64_t ldx, const uint8_t* q4_b200, con
     }
     if (flags & EETQ_B200_FLAG_FORCE_GEMV)
         EB_CHECK_ARG(M <= EETQ_B200_GEMV4_SIMT_MAX_M, "w4a16_gemm: FORCE_GEMV needs M <= %d", EETQ_B200_GEMV4_SIMT_MAX_M);
-    // measured (profiles/r02_kbench_mma2.json): one row streams fastest through the SIMT kernel (4096x4096: 5.4 vs 7.0 us); from two
-    // rows on the mma.sync kernel wins, by up to 1.7x at K = 11008 / 4 rows, and it also beats widening + tcgen05 up to 8 rows
+    // measured (profiles/r02_kbench_mma2.json): one row streams fastest through the SIMT kernel (4096x4096: 5.7 vs 6.8 us); from two
+    // rows on the mma.sync kernel wins, by up to 1.9x at K = 11008 / 4 rows, and it also beats widening + tcgen05 up to 8 rows
     if (M >= 2 && M <= EETQ_B200_GEMV4_MAX_M && !(flags & EETQ_B200_FLAG_FORCE_GEMV) && gemv_mma_on() && gemv_mma_supported(int(M), K, 4))
         return launch_gemv_mma(x, ldx, w4, scales, bias, nullptr, 0, y, ldy, int(M), N, K, dtype, 4, pdl, s);
     if (M <= EETQ_B200_GEMV4_SIMT_MAX_M) {
